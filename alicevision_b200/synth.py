@@ -1,0 +1,103 @@
+"""Deterministic synthetic regions for tests and bench (SURVEY.md §8(d) "Synthetic inputs").
+
+SIFT-like descriptors follow the reference extractor's quantisation (feature/sift/SIFT.hpp:80-110:
+RootSIFT ``floor(512*sqrt(x/sum x))``), so they are small non-negative integers and every squared
+L2 distance is an exact integer < 2^24 — the property that makes bit-exact index parity possible.
+MLDB-like descriptors are 486 random bits packed LSB-first into 64 bytes
+(feature/akaze/ImageDescriber_AKAZE.cpp:138-150).  numpy only; no product or oracle code here.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SEED_DATA = 20260922
+SEED_PAIRS = 7
+
+
+def _rootsift(raw: np.ndarray) -> np.ndarray:
+    x = raw / np.linalg.norm(raw, axis=1, keepdims=True)
+    x = np.minimum(x, 0.2)
+    x = x / np.linalg.norm(x, axis=1, keepdims=True)
+    return np.floor(512.0 * np.sqrt(x / x.sum(axis=1, keepdims=True)))
+
+
+def sift_pool(n: int, rng: np.random.Generator) -> np.ndarray:
+    return _rootsift(rng.gamma(0.6, 1.0, size=(n, 128)) + 1e-6).astype(np.int16)
+
+
+def positions(m: int, rng: np.random.Generator, generic: bool = True) -> np.ndarray:
+    """(m,2) float32 feature positions. generic=True: all x distinct and all y distinct (Appendix B)."""
+    if generic:
+        x = rng.permutation(m).astype(np.float32) + np.float32(0.25)
+        y = rng.permutation(m).astype(np.float32) + np.float32(0.5)
+    else:  # adversarial: duplicated (x,y), equal-x and equal-y collisions
+        x = rng.integers(0, max(m // 4, 2), m).astype(np.float32)
+        y = rng.integers(0, max(m // 4, 2), m).astype(np.float32)
+    return np.stack([x, y], axis=1)
+
+
+def sift_images(n_images: int, m: int, dtype=np.uint8, seed: int = SEED_DATA, shared: float = 0.4, noise: int = 4,
+                generic_positions: bool = True, pool_factor: float = 2.0):
+    """Returns (descs, xys): lists of (m,128) ``dtype`` arrays and (m,2) float32 positions.
+
+    Each image takes a seeded ~``shared`` fraction of a world pool (planted correspondences, +-noise per
+    component) and fills up to ``m`` with fresh descriptors.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pool = sift_pool(max(int(m * pool_factor), 8), rng)
+    descs, xys = [], []
+    for _ in range(n_images):
+        k = min(int(m * (shared + rng.uniform(-0.1, 0.1))), m, pool.shape[0])
+        sel = rng.choice(pool.shape[0], size=k, replace=False)
+        a = pool[sel].astype(np.int16) + rng.integers(-noise, noise + 1, size=(k, 128), dtype=np.int16)
+        a = np.clip(a, 0, 255)
+        b = sift_pool(m - k, rng) if m > k else np.zeros((0, 128), np.int16)
+        d = np.concatenate([a, np.clip(b, 0, 255)], axis=0)
+        d = d[rng.permutation(m)]
+        descs.append(np.ascontiguousarray(d.astype(dtype)))
+        xys.append(positions(m, rng, generic_positions))
+    return descs, xys
+
+
+def real_valued(descs, seed: int = 1, sigma: float = 0.37):
+    """Non-integer fp32 variant (exercises the exact, non-tensor-core path)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return [np.ascontiguousarray((d.astype(np.float32) + rng.normal(0, sigma, d.shape).astype(np.float32))) for d in descs]
+
+
+def mldb_images(n_images: int, m: int, seed: int = SEED_DATA, shared: float = 0.4, flip: float = 0.08, generic_positions: bool = True):
+    """Returns (descs, xys): (m,64) uint8 binary descriptors (486 used bits) + positions."""
+    rng = np.random.Generator(np.random.PCG64(seed ^ 0xB17))
+    def rnd(n):
+        bits = rng.integers(0, 2, size=(n, 512), dtype=np.uint8)
+        bits[:, 486:] = 0
+        return bits
+    pool = rnd(max(2 * m, 8))
+    descs, xys = [], []
+    for _ in range(n_images):
+        k = min(int(m * (shared + rng.uniform(-0.1, 0.1))), m)
+        sel = rng.choice(pool.shape[0], size=k, replace=False)
+        a = pool[sel] ^ (rng.random((k, 512)) < flip).astype(np.uint8)
+        a[:, 486:] = 0
+        bits = np.concatenate([a, rnd(m - k)], axis=0)[rng.permutation(m)]
+        descs.append(np.ascontiguousarray(np.packbits(bits, axis=1, bitorder="little")))
+        xys.append(positions(m, rng, generic_positions))
+    return descs, xys
+
+
+def exhaustive_pairs(n: int) -> np.ndarray:
+    """Upper-triangular pair list (matchingImageCollection/pairBuilder.cpp:22-46 with ids 0..n-1)."""
+    i, j = np.triu_indices(n, 1)
+    return np.stack([i, j], axis=1).astype(np.uint32)
+
+
+def voctree_like_pairs(n: int, k: int = 50, seed: int = SEED_PAIRS) -> np.ndarray:
+    """Synthetic stand-in for a vocabulary-tree pair list (imageMatching/ImageMatching.cpp:233-284 +
+    convertAllMatchesToPairList): k seeded neighbours per image, normalised to I<J, de-duplicated."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = set()
+    for i in range(n):
+        for j in rng.choice(n, size=min(k, n - 1), replace=False):
+            if int(j) != i:
+                s.add((min(i, int(j)), max(i, int(j))))
+    return np.array(sorted(s), np.uint32).reshape(-1, 2)
