@@ -1,0 +1,53 @@
+"""In-tree build of the native engine: nvcc -> alicevision_b200/libb200match.so (sm_100a only).
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot, so the box never compiles.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB = os.path.join(_HERE, "libb200match.so")
+SOURCES = ["engine.cu"]
+HEADERS = ["common.cuh", "ptx.cuh", "l2_tc.cuh", "l2_exact.cuh", "hamming.cuh", "prep.cuh", "verify.cuh", "../../include/b200match.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",   # explicit form: `-arch=sm_100a` also emits compute_100 PTX, which rejects tcgen05
+    "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA engine if sources are newer than the library. Returns the library path."""
+    if not force and not stale():
+        return LIB
+    env = dict(os.environ)
+    env.pop("CXX", None); env.pop("CC", None)       # the image exports a gcc wrapper without OpenMP specs; nvcc finds /usr/bin/g++
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force=True, verbose=True))

@@ -1,0 +1,56 @@
+// Device-side data model shared by the kernels of the descriptor-matching engine.
+// Names follow the reference's domain: views (images), regions/descriptors, pairs (I = database image,
+// J = query image; matching/RegionsMatcher.hpp:126-176), putative matches.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace b200m {
+
+enum : int { DT_F32 = 0, DT_U8 = 1, DT_BIN = 2 };
+
+// Per-view flag bits written by the prep kernel.
+enum : uint32_t {
+  VF_NONINTEGER = 1u,   // some component is not an integer
+  VF_RANGE = 2u,        // some |component| > 1024 (2v would not be exact in fp16)
+  VF_NORM = 4u,         // some squared norm >= 2^22 (distances would leave the exact-fp32 range)
+};
+
+// One uploaded view (image) resident in HBM.
+struct alignas(128) ViewDev {
+  CUtensorMap tmap;     // fp16 [m x 128], box {64 x 128}, SWIZZLE_128B (only when dim == 128 scalar)
+  const void* raw;      // original descriptors, row-major m x dim (f32 / u8 / 64-byte binary)
+  const __half* h16;    // fp16 copy (scalar, dim == 128) or nullptr
+  const float* nbh;     // ||row||^2 / 2, padded to a multiple of 256 rows with 1e30f
+  const float* nrm;     // ||row||^2
+  int32_t m;            // number of regions
+  int32_t dim;          // components (scalar) or bytes (binary)
+  int32_t dtype;
+  int32_t pad_;
+};
+static_assert(sizeof(ViewDev) % 128 == 0, "ViewDev must keep CUtensorMap 64-byte aligned in arrays");
+
+// One image pair of the current batch.
+struct PairDev {
+  uint32_t view_i, view_j;   // slots into the view table (I = database, J = query)
+  uint32_t m_i, m_j;
+  uint32_t cand_base;        // first candidate slot of this pair (prefix sum of m_j over the batch)
+  uint32_t mode;             // PM_*
+};
+enum : uint32_t { PM_TC = 0, PM_EXACT_F32 = 1, PM_EXACT_U8 = 2, PM_HAMMING = 3, PM_SKIP = 4 };
+
+// Work item of the tensor-core kernel: 128 consecutive queries of pair `pair` against the whole database image.
+struct WorkItem { uint32_t pair, qtile; };
+
+// Candidate produced by a search kernel, one per query that passed the (pre-)ratio test.
+//   PM_TC:   a = query row, b = 16-row chunk id of the best database row, d1 exact, d2 = upper bound (exactness pass needed)
+//   others:  a = query row, b = database row of the nearest neighbour, d1/d2 exact (float bits, or uint32 bits for Hamming)
+struct Cand { uint32_t q, b; float d1, d2; };
+
+// Raw match record handed to the host: i = database (I) feature, j = query (J) feature, the two smallest distances.
+// i == 0xFFFFFFFF marks a candidate dropped by the exactness pass.  For Hamming d1/d2 hold uint32 bit patterns.
+struct Rec { uint32_t i, j; float d1, d2; };
+
+}  // namespace b200m

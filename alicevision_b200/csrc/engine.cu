@@ -1,0 +1,745 @@
+// Host side of the engine behind the C ABI (include/b200match.h): view residency in HBM, pair batching,
+// kernel launches on one CUDA stream, record read-back and the host "finishing" stage that reproduces
+// RegionsMatcher::Match's tail (matching/RegionsMatcher.hpp:153-175) and the cross check
+// (matchingImageCollection/ImageCollectionMatcher_generic.cpp:83-111).
+//
+// There is deliberately no CPU search path in this file: every distance is computed by a CUDA kernel.
+#include "../../include/b200match.h"
+
+#include "common.cuh"
+#include "hamming.cuh"
+#include "l2_exact.cuh"
+#include "l2_tc.cuh"
+#include "prep.cuh"
+#include "verify.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <set>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace b200m;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(B200M_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ small thread pool
+class Pool {
+ public:
+  explicit Pool(int n) { resize(n); }
+  ~Pool() { stop(); }
+  void resize(int n) {
+    stop();
+    quit_ = false;
+    for (int i = 0; i < std::max(1, n); ++i) th_.emplace_back([this] { run(); });
+  }
+  void submit(std::function<void()> f) {
+    { std::lock_guard<std::mutex> l(mu_); q_.push(std::move(f)); ++pending_; }
+    cv_.notify_one();
+  }
+  void wait() { std::unique_lock<std::mutex> l(mu_); done_.wait(l, [this] { return pending_ == 0; }); }
+  int size() const { return (int)th_.size(); }
+
+ private:
+  void stop() {
+    { std::lock_guard<std::mutex> l(mu_); quit_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+    th_.clear();
+  }
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [this] { return quit_ || !q_.empty(); });
+        if (q_.empty()) return;
+        f = std::move(q_.front()); q_.pop();
+      }
+      f();
+      { std::lock_guard<std::mutex> l(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::queue<std::function<void()>> q_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  int pending_ = 0;
+  bool quit_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------ data model
+struct ViewHost {
+  uint32_t id = 0;
+  int m = 0, dim = 0, dtype = 0, m_pad = 0;
+  void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr;
+  std::vector<float> xy;      // m x 2 positions (host only; used by the finishing stage)
+  bool generic_pos = false;   // all x distinct and all y distinct
+  uint32_t flags = 0; bool flags_known = true;
+  bool tc_capable() const { return dtype != DT_BIN && dim == 128 && m > 0; }
+  bool tc_ok() const { return tc_capable() && flags == 0; }
+};
+
+struct BatchBuf {
+  PairDev* d_pairs = nullptr; WorkItem* d_items = nullptr; Cand* d_cands = nullptr; int* d_count = nullptr; int* d_off = nullptr;
+  Rec* d_out = nullptr;
+  PairDev* h_pairs = nullptr; WorkItem* h_items = nullptr; int* h_meta = nullptr; Rec* h_out = nullptr;   // pinned
+  cudaEvent_t ev_meta = nullptr, ev_copy = nullptr;
+};
+
+constexpr int PAIR_CAP = 4096;            // directed pairs per batch
+constexpr long CAND_CAP = 4l << 20;       // candidate slots per batch (sum of m_j)
+constexpr long ITEM_CAP = CAND_CAP / 64 + PAIR_CAP;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct b200m_ctx {
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  EncodeTiledFn encode = nullptr;
+  std::vector<ViewHost> views;
+  std::unordered_map<uint32_t, int> slot_of;
+  ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
+  BatchBuf buf[2]; bool bufs_ready = false;
+  unsigned int* d_err = nullptr;
+  std::vector<cudaEvent_t> tev;   // search-kernel timing events, reused across calls
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+  std::unique_ptr<Pool> pool;
+  bool force_exact = false;
+  // last-call instrumentation
+  double last_gpu_ms = 0, last_search_ms = 0; int last_launches = 0, last_tc_pairs = 0; int64_t last_records = 0;
+  unsigned err_total = 0;
+};
+
+struct b200m_db { b200m_ctx* ctx; ViewHost v; int metric; };
+
+struct b200m_result {
+  std::vector<uint32_t> pair_ids; std::vector<int64_t> offsets; std::vector<b200m_match> matches;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int alloc_view_buffers(b200m_ctx* c, ViewHost& v, const void* desc) {
+  const size_t esz = v.dtype == DT_F32 ? 4 : 1;
+  const size_t bytes = (size_t)v.m * v.dim * esz;
+  CK(cudaMallocAsync(&v.raw, std::max<size_t>(bytes, 256), c->stream));
+  CK(cudaMemcpyAsync(v.raw, desc, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (v.tc_capable()) {
+    v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
+    CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
+    CK(cudaMallocAsync((void**)&v.nbh, (size_t)v.m_pad * 4, c->stream));
+    CK(cudaMallocAsync((void**)&v.nrm, (size_t)v.m_pad * 4, c->stream));
+  }
+  return B200M_OK;
+}
+static void free_view_buffers(b200m_ctx* c, ViewHost& v) {
+  if (v.raw) cudaFreeAsync(v.raw, c->stream);
+  if (v.h16) cudaFreeAsync(v.h16, c->stream);
+  if (v.nbh) cudaFreeAsync(v.nbh, c->stream);
+  if (v.nrm) cudaFreeAsync(v.nrm, c->stream);
+  v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr;
+}
+
+static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.m = v.m; d.dim = v.dim; d.dtype = v.dtype;
+  if (v.tc_capable()) {
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)v.m};
+    const cuuint64_t gstr[1] = {256};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(&d.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.h16, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  }
+  return B200M_OK;
+}
+
+static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag) {
+  if (!v.tc_capable()) return B200M_OK;
+  const int grid = (v.m_pad + 7) / 8;
+  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag);
+  else prep_view_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag);
+  CK(cudaGetLastError());
+  return B200M_OK;
+}
+
+static bool positions_generic(const std::vector<float>& xy, int m) {
+  std::vector<float> xs(m), ys(m);
+  for (int i = 0; i < m; ++i) { xs[i] = xy[2 * i]; ys[i] = xy[2 * i + 1]; }
+  std::sort(xs.begin(), xs.end()); std::sort(ys.begin(), ys.end());
+  return std::adjacent_find(xs.begin(), xs.end()) == xs.end() && std::adjacent_find(ys.begin(), ys.end()) == ys.end();
+}
+
+static int ensure_view_capacity(b200m_ctx* c, int need) {
+  if (need <= c->view_cap) return B200M_OK;
+  int cap = std::max(256, c->view_cap * 2);
+  while (cap < need) cap *= 2;
+  ViewDev* nv = nullptr; uint32_t* nf = nullptr;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMalloc((void**)&nv, sizeof(ViewDev) * cap));
+  CK(cudaMalloc((void**)&nf, sizeof(uint32_t) * cap));
+  CK(cudaMemset(nf, 0, sizeof(uint32_t) * cap));
+  if (c->d_views) {
+    CK(cudaMemcpy(nv, c->d_views, sizeof(ViewDev) * c->view_cap, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nf, c->d_flags, sizeof(uint32_t) * c->view_cap, cudaMemcpyDeviceToDevice));
+    cudaFree(c->d_views); cudaFree(c->d_flags);
+  }
+  c->d_views = nv; c->d_flags = nf; c->view_cap = cap;
+  return B200M_OK;
+}
+
+static int ensure_batch_buffers(b200m_ctx* c) {
+  if (c->bufs_ready) return B200M_OK;
+  for (int s = 0; s < 2; ++s) {
+    BatchBuf& b = c->buf[s];
+    CK(cudaMalloc((void**)&b.d_pairs, sizeof(PairDev) * PAIR_CAP));
+    CK(cudaMalloc((void**)&b.d_items, sizeof(WorkItem) * ITEM_CAP));
+    CK(cudaMalloc((void**)&b.d_cands, sizeof(Cand) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_count, sizeof(int) * PAIR_CAP));
+    CK(cudaMalloc((void**)&b.d_off, sizeof(int) * (PAIR_CAP + 1)));
+    CK(cudaMalloc((void**)&b.d_out, sizeof(Rec) * CAND_CAP));
+    CK(cudaMallocHost((void**)&b.h_pairs, sizeof(PairDev) * PAIR_CAP));
+    CK(cudaMallocHost((void**)&b.h_items, sizeof(WorkItem) * ITEM_CAP));
+    CK(cudaMallocHost((void**)&b.h_meta, sizeof(int) * (2 * PAIR_CAP + 2)));
+    CK(cudaMallocHost((void**)&b.h_out, sizeof(Rec) * CAND_CAP));
+    CK(cudaEventCreateWithFlags(&b.ev_meta, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming));
+  }
+  CK(cudaFuncSetAttribute(tc::l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(exact_top2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
+  CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
+  CK(cudaFuncSetAttribute(exact_top2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
+  CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
+  c->bufs_ready = true;
+  return B200M_OK;
+}
+
+static cudaEvent_t timing_event(b200m_ctx* c, size_t& used) {
+  if (used == c->tev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->tev.push_back(e); }
+  return c->tev[used++];
+}
+
+// ------------------------------------------------------------------------------------------------ finishing (host)
+namespace {
+
+struct DecoKey { float x1, y1, x2, y2; b200m_match m; };
+// The reference's comparator (matching/IndMatchDecorator.hpp:34-49) is not a strict weak order; its effect is
+// defined by libstdc++'s std::set insertion walk, so the general path uses the same container with an
+// equivalent predicate: "a before b" iff they differ in some coordinate, their left x differ, and a.y1 < b.y1.
+struct DecoBefore {
+  bool operator()(const DecoKey& a, const DecoKey& b) const {
+    const bool same = a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2;
+    return !same && a.x1 != b.x1 && a.y1 < b.y1;
+  }
+};
+
+// recs -> final IndMatches of one directed pair.
+void finish_directed(const Rec* recs, int n, bool hamming, const ViewHost& vi, const ViewHost& vj, std::vector<b200m_match>& out) {
+  out.clear();
+  out.reserve(n);
+  for (int k = 0; k < n; ++k) {
+    const Rec& r = recs[k];
+    if (r.i == 0xFFFFFFFFu) continue;
+    b200m_match m;
+    m.i = r.i; m.j = r.j;                                    // IndMatch(i = database index, j = query index), RegionsMatcher.hpp:157-158
+    if (hamming) {
+      uint32_t d1, d2; std::memcpy(&d1, &r.d1, 4); std::memcpy(&d2, &r.d2, 4);
+      m.distance_ratio = (float)(d1 / d2);                   // integer division, matching/filters.hpp:64 on unsigned
+      m.distance = (float)d1;
+    } else {
+      m.distance_ratio = r.d1 / r.d2;                        // float division, filters.hpp:64
+      m.distance = r.d1;
+    }
+    out.push_back(m);
+  }
+  // IndMatch::getDeduplicated (IndMatch.hpp:52-58): every query j appears once, so this is a sort by (i, j).
+  std::sort(out.begin(), out.end(), [](const b200m_match& a, const b200m_match& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
+  if (out.empty()) return;
+  // IndMatchDecorator::getDeduplicated (IndMatchDecorator.hpp:57-69,84-98)
+  const float* xi = vi.xy.data(); const float* xj = vj.xy.data();
+  if (vi.generic_pos) {
+    // All left x distinct and all left y distinct: two matches are "equivalent" iff they share the left feature,
+    // the first inserted (smallest j) wins, and the in-order walk is ascending left y.
+    size_t w = 0;
+    for (size_t k = 0; k < out.size(); ++k)
+      if (k == 0 || out[k].i != out[k - 1].i) out[w++] = out[k];
+    out.resize(w);
+    std::sort(out.begin(), out.end(), [xi](const b200m_match& a, const b200m_match& b) { return xi[2 * a.i + 1] < xi[2 * b.i + 1]; });
+  } else {
+    std::vector<DecoKey> keys; keys.reserve(out.size());
+    for (const auto& m : out) keys.push_back(DecoKey{xi[2 * m.i], xi[2 * m.i + 1], xj[2 * m.j], xj[2 * m.j + 1], m});
+    std::set<DecoKey, DecoBefore> s(keys.begin(), keys.end());
+    out.clear();
+    for (const auto& k : s) out.push_back(k.m);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* b200m_last_error(void) { return g_err.c_str(); }
+int b200m_version(void) { return 100; }
+int b200m_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
+  if (!out) return fail(B200M_ERR_ARG, "out is null");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(B200M_ERR_CUDA, "no CUDA device: this engine has no CPU path"); }
+  if (device < 0 || device >= n) return fail(B200M_ERR_ARG, "bad device ordinal");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(B200M_ERR_UNSUPPORTED, "this build contains sm_100a code only (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")");
+  std::unique_ptr<b200m_ctx> c(new b200m_ctx());
+  c->device = device; c->num_sms = prop.multiProcessorCount;
+  if (stream) { c->stream = (cudaStream_t)stream; }
+  else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+  c->encode = (EncodeTiledFn)fn;
+  cudaMemPool_t mp;
+  CK(cudaDeviceGetDefaultMemPool(&mp, device));
+  uint64_t thr = ~0ull;
+  CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
+  CK(cudaMalloc((void**)&c->d_err, sizeof(unsigned int)));
+  CK(cudaMemset(c->d_err, 0, sizeof(unsigned int)));
+  CK(cudaEventCreate(&c->ev_start));
+  CK(cudaEventCreate(&c->ev_end));
+  int ht = (int)std::thread::hardware_concurrency();
+  c->pool.reset(new Pool(std::min(std::max(ht, 1), 32)));
+  *out = c.release();
+  return B200M_OK;
+}
+
+void b200m_ctx_destroy(b200m_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& v : c->views) free_view_buffers(c, v);
+  cudaStreamSynchronize(c->stream);
+  for (int s = 0; s < 2; ++s) {
+    BatchBuf& b = c->buf[s];
+    cudaFree(b.d_pairs); cudaFree(b.d_items); cudaFree(b.d_cands); cudaFree(b.d_count); cudaFree(b.d_off); cudaFree(b.d_out);
+    cudaFreeHost(b.h_pairs); cudaFreeHost(b.h_items); cudaFreeHost(b.h_meta); cudaFreeHost(b.h_out);
+    if (b.ev_meta) cudaEventDestroy(b.ev_meta);
+    if (b.ev_copy) cudaEventDestroy(b.ev_copy);
+  }
+  for (auto& e : c->tev) cudaEventDestroy(e);
+  cudaFree(c->d_views); cudaFree(c->d_flags); cudaFree(c->d_err);
+  cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
+  cudaStreamDestroy(c->copy_stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int b200m_ctx_set_host_threads(b200m_ctx* c, int n) {
+  if (!c || n < 1) return fail(B200M_ERR_ARG, "bad arguments");
+  c->pool->resize(std::min(n, 256));
+  return B200M_OK;
+}
+int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  c->force_exact = on != 0;
+  return B200M_OK;
+}
+
+// ---- Surface 2: views -------------------------------------------------------------------------------------------
+int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  if (n < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n > 0 && !desc)) return fail(B200M_ERR_ARG, "bad view arguments");
+  CK(cudaSetDevice(c->device));
+  int slot;
+  auto it = c->slot_of.find(view_id);
+  if (it == c->slot_of.end()) {
+    slot = (int)c->views.size();
+    int rc = ensure_view_capacity(c, slot + 1);
+    if (rc) return rc;
+    c->views.emplace_back();
+    c->slot_of[view_id] = slot;
+  } else {
+    slot = it->second;
+    free_view_buffers(c, c->views[slot]);
+  }
+  ViewHost& v = c->views[slot];
+  v = ViewHost();
+  v.id = view_id; v.m = n; v.dim = dim; v.dtype = dtype;
+  if (xy && n > 0) { v.xy.assign(xy, xy + 2 * (size_t)n); v.generic_pos = positions_generic(v.xy, n); }
+  if (n > 0) {
+    int rc = alloc_view_buffers(c, v, desc);
+    if (rc) return rc;
+    if (v.tc_capable()) {
+      CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->stream));
+      rc = run_prep(c, v, c->d_flags + slot);
+      if (rc) return rc;
+      v.flags_known = false;
+    }
+  }
+  ViewDev d;
+  int rc = make_view_dev(c, v, d);
+  if (rc) return rc;
+  // the source descriptor memory is caller-owned and pageable: make the H2D copies complete before returning
+  CK(cudaMemcpyAsync(c->d_views + slot, &d, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return B200M_OK;
+}
+
+int b200m_clear_views(b200m_ctx* c) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  CK(cudaSetDevice(c->device));
+  for (auto& v : c->views) free_view_buffers(c, v);
+  c->views.clear(); c->slot_of.clear();
+  CK(cudaStreamSynchronize(c->stream));
+  return B200M_OK;
+}
+
+// ---- Surface 2: pairs -------------------------------------------------------------------------------------------
+struct Directed { int slot_i, slot_j; uint32_t mode; int fwd_index; bool reverse; };
+
+int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out) {
+  if (!c || !out || n_pairs < 0 || (n_pairs > 0 && !pairs) || stage < 0 || stage > 2) return fail(B200M_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_batch_buffers(c);
+  if (rc) return rc;
+
+  // PairSet semantics (types.hpp:23): unique, lexicographically ordered.
+  std::set<std::pair<uint32_t, uint32_t>> ps;
+  for (int k = 0; k < n_pairs; ++k) ps.insert({pairs[2 * k], pairs[2 * k + 1]});
+  std::vector<std::pair<uint32_t, uint32_t>> fwd(ps.begin(), ps.end());
+
+  // exactness flags of freshly uploaded views
+  bool need_flags = false;
+  for (auto& v : c->views) need_flags |= !v.flags_known;
+  if (need_flags) {
+    std::vector<uint32_t> hf(c->views.size());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(hf.data(), c->d_flags, 4 * hf.size(), cudaMemcpyDeviceToHost));
+    for (size_t s = 0; s < c->views.size(); ++s) if (!c->views[s].flags_known) { c->views[s].flags = hf[s]; c->views[s].flags_known = true; }
+  }
+
+  const bool do_cross = cross != 0 && stage == B200M_STAGE_FULL;
+  std::vector<Directed> dir;
+  dir.reserve(fwd.size() * (do_cross ? 2 : 1));
+  int tc_pairs = 0;
+  for (size_t k = 0; k < fwd.size(); ++k) {
+    auto si = c->slot_of.find(fwd[k].first), sj = c->slot_of.find(fwd[k].second);
+    if (si == c->slot_of.end() || sj == c->slot_of.end())
+      return fail(B200M_ERR_ARG, "pair references a view that was never uploaded (RegionsPerView::getRegions would throw std::out_of_range)");
+    for (int rev = 0; rev < (do_cross ? 2 : 1); ++rev) {
+      const int a = rev ? sj->second : si->second, b = rev ? si->second : sj->second;   // a = database, b = query
+      const ViewHost& vi = c->views[a]; const ViewHost& vj = c->views[b];
+      uint32_t mode;
+      if (vi.m == 0 || vj.m == 0 || vi.dtype != vj.dtype || vi.dim != vj.dim) mode = PM_SKIP;           // generic.cpp:59-63,74-78
+      else if (vi.m < 2) mode = PM_SKIP;                                                                 // NN=2 > rows: bruteForce.hpp:105
+      else if (vi.dtype == DT_BIN) {
+        if (vi.dim != 64) return fail(B200M_ERR_UNSUPPORTED, "binary descriptors must be 64 bytes (AKAZE_BinaryRegions)");
+        mode = PM_HAMMING;
+      } else {
+        if (vi.dim != 128) return fail(B200M_ERR_UNSUPPORTED, "scalar descriptors must have 128 components on the collection surface");
+        if (!c->force_exact && vi.tc_ok() && vj.tc_ok()) { mode = PM_TC; ++tc_pairs; }
+        else mode = vi.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8;
+      }
+      if (stage == B200M_STAGE_FULL && mode != PM_SKIP && (vi.xy.empty() || vj.xy.empty()))
+        return fail(B200M_ERR_ARG, "B200M_STAGE_FULL needs feature positions for every matched view");
+      dir.push_back(Directed{a, b, mode, (int)k, rev != 0});
+    }
+  }
+
+  // ---- batching
+  struct Batch { size_t begin, end; };
+  std::vector<Batch> batches;
+  {
+    size_t b0 = 0; long cand = 0, items = 0;
+    const size_t step = do_cross ? 2 : 1;
+    for (size_t k = 0; k < dir.size(); k += step) {
+      long need_c = 0, need_i = 0;
+      for (size_t u = k; u < k + step; ++u) {
+        const int mj = c->views[dir[u].slot_j].m;
+        if (mj > CAND_CAP) return fail(B200M_ERR_UNSUPPORTED, "view too large for one batch");
+        need_c += mj; need_i += (mj + tc::BM - 1) / tc::BM;
+      }
+      if (k > b0 && (cand + need_c > CAND_CAP || items + need_i > ITEM_CAP || k - b0 + step > (size_t)PAIR_CAP)) {
+        batches.push_back({b0, k}); b0 = k; cand = 0; items = 0;
+      }
+      cand += need_c; items += need_i;
+    }
+    if (dir.size() > b0) batches.push_back({b0, dir.size()});
+  }
+
+  const float ratio_sq = dist_ratio * dist_ratio;   // Square(f_dist_ratio) in float, RegionsMatcher.hpp:150 / numeric.hpp:130
+  std::vector<std::vector<b200m_match>> per_dir(stage == B200M_STAGE_DEVICE ? 0 : dir.size());
+  size_t tev_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+  int launches = 0;
+  int64_t total_records = 0;
+  c->pool->wait();
+
+  auto enqueue = [&](size_t bi) -> int {
+    const Batch& B = batches[bi];
+    BatchBuf& bb = c->buf[bi & 1];
+    const int np = (int)(B.end - B.begin);
+    uint32_t cbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
+    bool any_f32 = false, any_u8 = false, any_ham = false;
+    for (int p = 0; p < np; ++p) {
+      const Directed& d = dir[B.begin + p];
+      const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
+      bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, d.mode};
+      cbase += (uint32_t)vj.m;
+      if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + tc::BM - 1) / tc::BM; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
+      if (d.mode == PM_EXACT_F32) { any_f32 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
+      if (d.mode == PM_EXACT_U8) { any_u8 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
+      if (d.mode == PM_HAMMING) { any_ham = true; max_qblk_ham = std::max(max_qblk_ham, (vj.m + HM_TQ - 1) / HM_TQ); }
+    }
+    CK(cudaMemcpyAsync(bb.d_pairs, bb.h_pairs, sizeof(PairDev) * np, cudaMemcpyHostToDevice, c->stream));
+    if (n_items) CK(cudaMemcpyAsync(bb.d_items, bb.h_items, sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(bb.d_count, 0, sizeof(int) * np, c->stream));
+    cudaEvent_t k0 = timing_event(c, tev_used), k1 = timing_event(c, tev_used);
+    CK(cudaEventRecord(k0, c->stream));
+    if (n_items) {
+      const int grid = std::min(n_items, c->num_sms);
+      tc::l2_top2_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq);
+      ++launches;
+    }
+    if (any_f32) {
+      exact_top2_kernel<float, false><<<dim3(max_qblk_exact, np), 256, EX_SMEM, c->stream>>>(c->d_views, bb.d_pairs, PM_EXACT_F32, bb.d_cands, bb.d_count, ratio_sq, nullptr, nullptr);
+      ++launches;
+    }
+    if (any_u8) {
+      exact_top2_kernel<uint8_t, false><<<dim3(max_qblk_exact, np), 256, EX_SMEM, c->stream>>>(c->d_views, bb.d_pairs, PM_EXACT_U8, bb.d_cands, bb.d_count, ratio_sq, nullptr, nullptr);
+      ++launches;
+    }
+    if (any_ham) {
+      hamming_top2_kernel<false><<<dim3(max_qblk_ham, np), HM_TQ, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, dist_ratio, nullptr, nullptr);
+      ++launches;
+    }
+    CK(cudaEventRecord(k1, c->stream));
+    kernel_events.push_back({k0, k1});
+    scan_counts_kernel<<<1, 1024, 0, c->stream>>>(bb.d_count, np, bb.d_off);
+    verify_pack_kernel<<<dim3(np, VERIFY_BLOCKS_PER_PAIR), VERIFY_WARPS * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, bb.d_off, bb.d_out, ratio_sq, c->d_err);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bb.h_meta, bb.d_count, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(bb.h_meta + PAIR_CAP, bb.d_off, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(bb.ev_meta, c->stream));
+    return B200M_OK;
+  };
+
+  CK(cudaEventRecord(c->ev_start, c->stream));
+  if (stage == B200M_STAGE_DEVICE) {
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+      if (bi >= 2) CK(cudaEventSynchronize(c->buf[bi & 1].ev_meta));   // pinned staging of batch bi-2 consumed by its H2D copies
+      if ((rc = enqueue(bi))) return rc;
+      // totals are read from the pinned meta buffer once the batch is done; accumulate lazily below
+      if (bi >= 1) { CK(cudaEventSynchronize(c->buf[(bi - 1) & 1].ev_meta)); const Batch& P = batches[bi - 1]; total_records += c->buf[(bi - 1) & 1].h_meta[PAIR_CAP + (P.end - P.begin)]; }
+    }
+    CK(cudaEventRecord(c->ev_end, c->stream));
+    if (!batches.empty()) { const size_t l = batches.size() - 1; CK(cudaEventSynchronize(c->buf[l & 1].ev_meta)); total_records += c->buf[l & 1].h_meta[PAIR_CAP + (batches[l].end - batches[l].begin)]; }
+  } else {
+    if (!batches.empty() && (rc = enqueue(0))) return rc;
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+      const Batch& B = batches[bi];
+      BatchBuf& bb = c->buf[bi & 1];
+      const int np = (int)(B.end - B.begin);
+      if (bi + 1 < batches.size()) {
+        // buffer set (bi+1)&1 was last used by batch bi-1: its records have been consumed (pool wait below)
+        if ((rc = enqueue(bi + 1))) return rc;
+      } else {
+        CK(cudaEventRecord(c->ev_end, c->stream));
+      }
+      CK(cudaEventSynchronize(bb.ev_meta));
+      const int total = bb.h_meta[PAIR_CAP + np];
+      if (total > 0) {
+        CK(cudaStreamWaitEvent(c->copy_stream, bb.ev_meta, 0));
+        CK(cudaMemcpyAsync(bb.h_out, bb.d_out, sizeof(Rec) * (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(bb.ev_copy, c->copy_stream));
+        CK(cudaEventSynchronize(bb.ev_copy));
+      }
+      total_records += total;
+      // finishing tasks (one per directed pair) — they read bb.h_out, so they must finish before batch bi+2 copies into it
+      for (int p = 0; p < np; ++p) {
+        const size_t di = B.begin + p;
+        const Directed d = dir[di];
+        if (d.mode == PM_SKIP) continue;
+        const int cnt = bb.h_meta[p];
+        const Rec* recs = bb.h_out + bb.h_meta[PAIR_CAP + p];
+        std::vector<b200m_match>* dst = &per_dir[di];
+        const ViewHost* vi = &c->views[d.slot_i]; const ViewHost* vj = &c->views[d.slot_j];
+        const bool ham = d.mode == PM_HAMMING;
+        if (stage == B200M_STAGE_FULL) {
+          c->pool->submit([=] { finish_directed(recs, cnt, ham, *vi, *vj, *dst); });
+        } else {
+          c->pool->submit([=] {
+            dst->clear();
+            for (int k = 0; k < cnt; ++k) {
+              const Rec& r = recs[k];
+              if (r.i == 0xFFFFFFFFu) continue;
+              b200m_match m; m.i = r.i; m.j = r.j;
+              if (ham) { uint32_t d1, d2; std::memcpy(&d1, &r.d1, 4); std::memcpy(&d2, &r.d2, 4); m.distance_ratio = (float)(d1 / d2); m.distance = (float)d1; }
+              else { m.distance_ratio = r.d1 / r.d2; m.distance = r.d1; }
+              dst->push_back(m);
+            }
+          });
+        }
+      }
+      c->pool->wait();
+    }
+    if (batches.empty()) CK(cudaEventRecord(c->ev_end, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_end));
+  c->last_gpu_ms = ms;
+  double sk = 0;
+  for (auto& e : kernel_events) { float t = 0.f; CK(cudaEventElapsedTime(&t, e.first, e.second)); sk += t; }
+  c->last_search_ms = sk; c->last_launches = launches; c->last_tc_pairs = tc_pairs; c->last_records = total_records;
+  unsigned errs = 0;
+  CK(cudaMemcpy(&errs, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  c->err_total = errs;
+
+  // ---- assemble
+  std::unique_ptr<b200m_result> res(new b200m_result());
+  res->pair_ids.reserve(2 * fwd.size());
+  res->offsets.reserve(fwd.size() + 1);
+  res->offsets.push_back(0);
+  const size_t step = do_cross ? 2 : 1;
+  for (size_t k = 0; k < fwd.size(); ++k) {
+    res->pair_ids.push_back(fwd[k].first); res->pair_ids.push_back(fwd[k].second);
+    if (stage != B200M_STAGE_DEVICE) {
+      std::vector<b200m_match>& f = per_dir[k * step];
+      if (do_cross) {
+        // keep m iff (m.j, m.i) is in the reverse list (ImageCollectionMatcher_generic.cpp:92-109)
+        std::vector<std::pair<uint32_t, uint32_t>> rv;
+        rv.reserve(per_dir[k * step + 1].size());
+        for (auto& m : per_dir[k * step + 1]) rv.push_back({m.i, m.j});
+        std::sort(rv.begin(), rv.end());
+        for (auto& m : f)
+          if (std::binary_search(rv.begin(), rv.end(), std::make_pair(m.j, m.i))) res->matches.push_back(m);
+      } else {
+        res->matches.insert(res->matches.end(), f.begin(), f.end());
+      }
+    }
+    res->offsets.push_back((int64_t)res->matches.size());
+  }
+  *out = res.release();
+  return B200M_OK;
+}
+
+int b200m_result_num_pairs(const b200m_result* r) { return r ? (int)(r->offsets.size() - 1) : 0; }
+int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int64_t** offsets, const b200m_match** matches) {
+  if (!r) return fail(B200M_ERR_ARG, "result is null");
+  if (pair_ids) *pair_ids = r->pair_ids.data();
+  if (offsets) *offsets = r->offsets.data();
+  if (matches) *matches = r->matches.data();
+  return B200M_OK;
+}
+void b200m_result_free(b200m_result* r) { delete r; }
+
+double b200m_last_gpu_ms(const b200m_ctx* c) { return c ? c->last_gpu_ms : 0; }
+double b200m_last_search_kernel_ms(const b200m_ctx* c) { return c ? c->last_search_ms : 0; }
+int b200m_last_launches(const b200m_ctx* c) { return c ? c->last_launches : 0; }
+int b200m_last_tc_pairs(const b200m_ctx* c) { return c ? c->last_tc_pairs : 0; }
+unsigned b200m_exactness_errors(const b200m_ctx* c) { return c ? c->err_total : 0; }
+int64_t b200m_last_records(const b200m_ctx* c) { return c ? c->last_records : 0; }
+
+// ---- Surface 1: ArrayMatcher ------------------------------------------------------------------------------------
+int b200m_db_create(b200m_ctx* c, const void* data, int rows, int dim, int dtype, int metric, b200m_db** out) {
+  if (!c || !out) return fail(B200M_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  if (rows < 1) return fail(B200M_ERR_EMPTY, "Build: nbRows < 1 (ArrayMatcher_bruteForce.hpp:44-48)");
+  if (!data || dim < 1 || dtype < 0 || dtype > 2 || metric < 0 || metric > 2) return fail(B200M_ERR_ARG, "bad database arguments");
+  if ((metric == B200M_HAMMING) != (dtype == B200M_BIN)) return fail(B200M_ERR_ARG, "Hamming metric needs binary descriptors and vice versa");
+  CK(cudaSetDevice(c->device));
+  std::unique_ptr<b200m_db> db(new b200m_db());
+  db->ctx = c; db->metric = metric;
+  db->v.m = rows; db->v.dim = dim; db->v.dtype = dtype;
+  const size_t esz = dtype == DT_F32 ? 4 : 1;
+  CK(cudaMalloc(&db->v.raw, std::max<size_t>((size_t)rows * dim * esz, 256)));
+  CK(cudaMemcpy(db->v.raw, data, (size_t)rows * dim * esz, cudaMemcpyHostToDevice));
+  *out = db.release();
+  return B200M_OK;
+}
+void b200m_db_destroy(b200m_db* db) {
+  if (!db) return;
+  cudaSetDevice(db->ctx->device);
+  cudaFree(db->v.raw);
+  delete db;
+}
+
+int b200m_knn(b200m_ctx* c, const b200m_db* db, const void* query, int nq, int nn, int32_t* idx, void* dist) {
+  if (!c || !db) return fail(B200M_ERR_ARG, "matcher not built (ArrayMatcher_bruteForce.hpp:100-103)");
+  if (nn < 1 || nn > db->v.m || nq < 1) return fail(B200M_ERR_ARG, "NN > rows or nbQuery < 1 (ArrayMatcher_bruteForce.hpp:105-108)");
+  if (nn > GEN_MAX_NN) return fail(B200M_ERR_UNSUPPORTED, "NN > 16 is not supported");
+  if (!query || !idx || !dist) return fail(B200M_ERR_ARG, "null buffers");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_batch_buffers(c);
+  if (rc) return rc;
+  const ViewHost& v = db->v;
+  const size_t esz = v.dtype == DT_F32 ? 4 : 1;
+  void* d_q = nullptr; int32_t* d_idx = nullptr; uint32_t* d_dist = nullptr;
+  CK(cudaMallocAsync(&d_q, std::max<size_t>((size_t)nq * v.dim * esz, 256), c->stream));
+  CK(cudaMallocAsync((void**)&d_idx, sizeof(int32_t) * (size_t)nq * nn, c->stream));
+  CK(cudaMallocAsync((void**)&d_dist, sizeof(uint32_t) * (size_t)nq * nn, c->stream));
+  CK(cudaMemcpyAsync(d_q, query, (size_t)nq * v.dim * esz, cudaMemcpyHostToDevice, c->stream));
+  const bool tiled_l2 = nn == 2 && v.dim == 128 && v.dtype != DT_BIN && (v.dtype == DT_U8 || db->metric == B200M_L2_VECTORIZED);
+  const bool tiled_ham = nn == 2 && v.dim == 64 && v.dtype == DT_BIN;
+  if (tiled_l2 || tiled_ham) {
+    ViewDev hv[2]; std::memset(hv, 0, sizeof(hv));
+    hv[0].raw = v.raw; hv[0].m = v.m; hv[0].dim = v.dim; hv[0].dtype = v.dtype;
+    hv[1].raw = d_q; hv[1].m = nq; hv[1].dim = v.dim; hv[1].dtype = v.dtype;
+    const uint32_t mode = tiled_ham ? PM_HAMMING : (v.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8);
+    PairDev hp{0u, 1u, (uint32_t)v.m, (uint32_t)nq, 0u, mode};
+    ViewDev* d_v = nullptr; PairDev* d_p = nullptr;
+    CK(cudaMallocAsync((void**)&d_v, sizeof(hv), c->stream));
+    CK(cudaMallocAsync((void**)&d_p, sizeof(hp), c->stream));
+    CK(cudaMemcpyAsync(d_v, hv, sizeof(hv), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_p, &hp, sizeof(hp), cudaMemcpyHostToDevice, c->stream));
+    if (tiled_ham) hamming_top2_kernel<true><<<dim3((nq + HM_TQ - 1) / HM_TQ, 1), HM_TQ, 0, c->stream>>>(d_v, d_p, nullptr, nullptr, 0.f, d_idx, d_dist);
+    else if (v.dtype == DT_F32) exact_top2_kernel<float, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, c->stream>>>(d_v, d_p, mode, nullptr, nullptr, 0.f, d_idx, (float*)d_dist);
+    else exact_top2_kernel<uint8_t, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, c->stream>>>(d_v, d_p, mode, nullptr, nullptr, 0.f, d_idx, (float*)d_dist);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // hv/hp are stack objects
+    cudaFreeAsync(d_v, c->stream); cudaFreeAsync(d_p, c->stream);
+  } else {
+    const int grid = (nq + 3) / 4;
+    if (v.dtype == DT_F32) generic_knn_kernel<float><<<grid, 128, 0, c->stream>>>((const float*)v.raw, v.m, (const float*)d_q, nq, v.dim, nn, db->metric, d_idx, d_dist);
+    else generic_knn_kernel<uint8_t><<<grid, 128, 0, c->stream>>>((const uint8_t*)v.raw, v.m, (const uint8_t*)d_q, nq, v.dim, nn, db->metric, d_idx, d_dist);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(dist, d_dist, sizeof(uint32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFreeAsync(d_q, c->stream); cudaFreeAsync(d_idx, c->stream); cudaFreeAsync(d_dist, c->stream);
+  return B200M_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Python host-side mirror of the reference interface for the descriptor-matching path, over the C ABI.
+
+The product is the C-ABI library (include/b200match.h) plus the C++ adaptors in alicevision_b200/adaptor/.
+This module binds the same C entry points with ctypes so that the parity tests and the bench read like the
+reference's own tests (same method names and argument meaning):
+
+* ``ArrayMatcherB200``            <->  matching::ArrayMatcher<Scalar,Metric>      (matching/ArrayMatcher.hpp:19-66)
+* ``ImageCollectionMatcherB200``  <->  matchingImageCollection::IImageCollectionMatcher (IImageCollectionMatcher.hpp:28-42)
+* ``EMatcherType``                <->  matching::EMatcherType                      (matching/matcherType.hpp:15-22)
+
+Nothing here computes distances: if the CUDA library is missing or no GPU is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from enum import IntEnum
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200match.so")
+
+F32, U8, BIN = 0, 1, 2
+L2_SIMPLE, L2_VECTORIZED, HAMMING = 0, 1, 2
+STAGE_DEVICE, STAGE_RAW, STAGE_FULL = 0, 1, 2
+
+MATCH_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("ratio", np.float32), ("dist", np.float32)])
+
+# every symbol include/b200match.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
+    "b200m_ctx_set_force_exact", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_clear_views",
+    "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
+    "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
+]
+
+
+class EMatcherType(IntEnum):
+    """matching/matcherType.hpp:15-22 plus the two values an integration adds for this engine."""
+    BRUTE_FORCE_L2 = 0
+    ANN_L2 = 1
+    CASCADE_HASHING_L2 = 2
+    FAST_CASCADE_HASHING_L2 = 3
+    BRUTE_FORCE_HAMMING = 4
+    BRUTE_FORCE_L2_B200 = 5
+    BRUTE_FORCE_HAMMING_B200 = 6
+
+
+class B200MatchError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libb200match.so (no fallback: a missing library is an error)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200MatchError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.b200m_last_error.restype = C.c_char_p
+    lib.b200m_last_gpu_ms.restype = C.c_double
+    lib.b200m_last_search_kernel_ms.restype = C.c_double
+    lib.b200m_last_records.restype = C.c_int64
+    lib.b200m_exactness_errors.restype = C.c_uint
+    for name in ("b200m_ctx_destroy", "b200m_db_destroy", "b200m_result_free"):
+        getattr(lib, name).restype = None
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200MatchError(f"{what} failed (status {rc}): {load_library().b200m_last_error().decode()}")
+
+
+def _dtype_code(a: np.ndarray, binary: bool) -> int:
+    if a.dtype == np.float32:
+        return F32
+    if a.dtype == np.uint8:
+        return BIN if binary else U8
+    raise TypeError(f"unsupported descriptor dtype {a.dtype} (float32 / uint8 only)")
+
+
+class Context:
+    """One engine instance bound to one GPU (``b200m_ctx``)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        _check(self.lib.b200m_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h)), "b200m_ctx_create")
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.b200m_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_host_threads(self, n: int) -> None:
+        _check(self.lib.b200m_ctx_set_host_threads(self._h, C.c_int(n)), "b200m_ctx_set_host_threads")
+
+    def set_force_exact(self, on: bool) -> None:
+        _check(self.lib.b200m_ctx_set_force_exact(self._h, C.c_int(int(on))), "b200m_ctx_set_force_exact")
+
+    # instrumentation
+    def last_gpu_ms(self) -> float: return self.lib.b200m_last_gpu_ms(self._h)
+    def last_search_kernel_ms(self) -> float: return self.lib.b200m_last_search_kernel_ms(self._h)
+    def last_launches(self) -> int: return self.lib.b200m_last_launches(self._h)
+    def last_tc_pairs(self) -> int: return self.lib.b200m_last_tc_pairs(self._h)
+    def exactness_errors(self) -> int: return self.lib.b200m_exactness_errors(self._h)
+    def last_records(self) -> int: return self.lib.b200m_last_records(self._h)
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class ArrayMatcherB200:
+    """Mirror of matching::ArrayMatcher (Build / SearchNeighbour / SearchNeighbours), bool returns, no exceptions
+    on the matcher surface (ArrayMatcher_bruteForce.hpp:42-51,63-85,98-142)."""
+
+    def __init__(self, metric: int = L2_SIMPLE, ctx: Context | None = None, binary: bool = False):
+        self.ctx = ctx or default_context()
+        self.metric = HAMMING if binary else metric
+        self.binary = binary
+        self._db = C.c_void_p()
+        self._dim = 0
+        self._dtype = None
+
+    def Build(self, dataset: np.ndarray, nbRows: int | None = None, dimension: int | None = None) -> bool:
+        self._release()
+        a = np.ascontiguousarray(dataset)
+        rows = a.shape[0] if nbRows is None else nbRows
+        dim = (a.shape[1] if a.ndim == 2 else 0) if dimension is None else dimension
+        if rows < 1:
+            return False
+        rc = self.ctx.lib.b200m_db_create(self.ctx._h, a.ctypes.data_as(C.c_void_p), C.c_int(rows), C.c_int(dim),
+                                          C.c_int(_dtype_code(a, self.binary)), C.c_int(self.metric), C.byref(self._db))
+        self._dim, self._dtype = dim, a.dtype
+        return rc == 0
+
+    def SearchNeighbours(self, query: np.ndarray, nbQuery: int | None = None, NN: int = 2):
+        """Returns (ok, indices[nq,NN] int32 database rows, distances[nq,NN] float32|uint32)."""
+        q = np.ascontiguousarray(query, dtype=self._dtype) if self._dtype is not None else np.ascontiguousarray(query)
+        nq = (q.shape[0] if q.ndim == 2 else (1 if q.size else 0)) if nbQuery is None else nbQuery
+        idx = np.zeros((max(nq, 1), NN), np.int32)
+        dist = np.zeros((max(nq, 1), NN), np.uint32 if self.metric == HAMMING else np.float32)
+        if not self._db:
+            return False, idx[:0], dist[:0]
+        rc = self.ctx.lib.b200m_knn(self.ctx._h, self._db, q.ctypes.data_as(C.c_void_p), C.c_int(nq), C.c_int(NN),
+                                    idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            return False, idx[:0], dist[:0]
+        return True, idx[:nq], dist[:nq]
+
+    def SearchNeighbour(self, query: np.ndarray):
+        """Single nearest neighbour: returns (ok, index, distance)."""
+        ok, idx, dist = self.SearchNeighbours(np.ascontiguousarray(query).reshape(1, -1), 1, 1)
+        if not ok:
+            return False, -1, -1.0
+        return True, int(idx[0, 0]), dist[0, 0]
+
+    def _release(self):
+        if self._db:
+            self.ctx.lib.b200m_db_destroy(self._db)
+            self._db = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+class ImageCollectionMatcherB200:
+    """Mirror of IImageCollectionMatcher / ImageCollectionMatcher_generic (distRatio, crossMatching, matcherType)."""
+
+    def __init__(self, distRatio: float = 0.8, crossMatching: bool = False, matcherType: EMatcherType = EMatcherType.BRUTE_FORCE_L2_B200,
+                 ctx: Context | None = None):
+        if matcherType not in (EMatcherType.BRUTE_FORCE_L2_B200, EMatcherType.BRUTE_FORCE_HAMMING_B200, EMatcherType.BRUTE_FORCE_L2,
+                               EMatcherType.BRUTE_FORCE_HAMMING):
+            raise IndexError("Invalid matcherType enum")    # matchingCommon.cpp:41-42 throws std::out_of_range
+        self.ctx = ctx or default_context()
+        self.distRatio, self.crossMatching, self.matcherType = float(distRatio), bool(crossMatching), matcherType
+        self.hamming = matcherType in (EMatcherType.BRUTE_FORCE_HAMMING_B200, EMatcherType.BRUTE_FORCE_HAMMING)
+
+    def upload(self, regionsPerView: dict) -> None:
+        """regionsPerView: {viewId: (descriptors[n,dim], positions[n,2] or None)} for ONE descriptor type."""
+        lib = self.ctx.lib
+        for vid, (desc, xy) in regionsPerView.items():
+            d = np.ascontiguousarray(desc)
+            n = d.shape[0]
+            dim = d.shape[1] if d.ndim == 2 else 0
+            binary = d.dtype == np.uint8 and self.hamming
+            xyp = None
+            if xy is not None:
+                xya = np.ascontiguousarray(xy, np.float32)
+                xyp = xya.ctypes.data_as(C.c_void_p)
+            _check(lib.b200m_upload_view(self.ctx._h, C.c_uint32(vid), d.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(max(dim, 1)),
+                                         C.c_int(_dtype_code(d, binary)), xyp), "b200m_upload_view")
+
+    def clear(self) -> None:
+        _check(self.ctx.lib.b200m_clear_views(self.ctx._h), "b200m_clear_views")
+
+    def match_uploaded(self, pairs, stage: int = STAGE_FULL):
+        """Runs b200m_match_pairs on already-uploaded views. Returns (pair_ids[n,2], offsets[n+1], matches[MATCH_DTYPE])."""
+        lib = self.ctx.lib
+        p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        res = C.c_void_p()
+        _check(lib.b200m_match_pairs(self.ctx._h, p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_float(self.distRatio),
+                                     C.c_int(int(self.crossMatching)), C.c_int(stage), C.byref(res)), "b200m_match_pairs")
+        try:
+            n = lib.b200m_result_num_pairs(res)
+            pid, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _check(lib.b200m_result_get(res, C.byref(pid), C.byref(off), C.byref(mat)), "b200m_result_get")
+            offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), (n + 1,)).copy() if n >= 0 else np.zeros(1, np.int64)
+            pair_ids = np.ctypeslib.as_array(C.cast(pid, C.POINTER(C.c_uint32)), (n, 2)).copy() if n else np.zeros((0, 2), np.uint32)
+            total = int(offsets[-1])
+            if total:
+                raw = np.ctypeslib.as_array(C.cast(mat, C.POINTER(C.c_uint8)), (total * MATCH_DTYPE.itemsize,)).copy()
+                matches = raw.view(MATCH_DTYPE)
+            else:
+                matches = np.zeros(0, MATCH_DTYPE)
+        finally:
+            lib.b200m_result_free(res)
+        return pair_ids, offsets, matches
+
+    def Match(self, regionsPerView: dict, pairs, map_PutativesMatches: dict | None = None) -> dict:
+        """IImageCollectionMatcher::Match: appends {(I, J): matches} for every pair with a non-empty result
+        (ImageCollectionMatcher_generic.cpp:116-119: empty lists are not inserted; the output map is appended to)."""
+        out = {} if map_PutativesMatches is None else map_PutativesMatches
+        self.upload(regionsPerView)
+        pair_ids, offsets, matches = self.match_uploaded(pairs, STAGE_FULL)
+        for k in range(pair_ids.shape[0]):
+            a, b = int(offsets[k]), int(offsets[k + 1])
+            if b > a:
+                out[(int(pair_ids[k, 0]), int(pair_ids[k, 1]))] = matches[a:b].copy()
+        return out
+
+
+def createImageCollectionMatcher(matcherType: EMatcherType, distRatio: float, crossMatching: bool, ctx: Context | None = None):
+    """matchingImageCollection/matchingCommon.cpp:19-47 restricted to the matcher types this engine implements."""
+    return ImageCollectionMatcherB200(distRatio, crossMatching, matcherType, ctx)

@@ -1,0 +1,107 @@
+/*
+ * b200match — C ABI of the Blackwell (sm_100a) descriptor-matching engine.
+ *
+ * Drop-in boundary for the one hot path of AliceVision's featureMatching step.  Every entry point below is what
+ * a reference-side adaptor binds (see INTEGRATION.md and alicevision_b200/adaptor/):
+ *
+ *   Surface 1  matching::ArrayMatcher<Scalar,Metric>         src/aliceVision/matching/ArrayMatcher.hpp:39,51,65
+ *              (reference implementation replaced: ArrayMatcher_bruteForce.hpp:42-142)
+ *   Surface 2  matchingImageCollection::IImageCollectionMatcher::Match
+ *                                                            src/aliceVision/matchingImageCollection/IImageCollectionMatcher.hpp:36-41
+ *              (reference implementation replaced: ImageCollectionMatcher_generic.cpp:30-123 with
+ *               matching/RegionsMatcher.hpp:126-176 inside)
+ *
+ * Plain pointers and sizes only.  All functions return 0 on success, non-zero on failure (never throw, never
+ * abort); b200m_last_error() returns a thread-local message.  There is NO CPU fallback inside the library: without
+ * a CUDA device every compute entry point fails with B200M_ERR_CUDA.
+ */
+#ifndef B200MATCH_H_
+#define B200MATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200m_ctx b200m_ctx;       /* one engine instance bound to one GPU */
+typedef struct b200m_db b200m_db;         /* a built ArrayMatcher database (Surface 1) */
+typedef struct b200m_result b200m_result; /* output of b200m_match_pairs (Surface 2) */
+
+/* descriptor element types: feature::Regions::Type_id() "f" / "h" and IsBinary() (feature/Regions.hpp:157-161) */
+enum { B200M_F32 = 0, B200M_U8 = 1, B200M_BIN = 2 };
+/* metrics: feature::L2_Simple (metric.hpp:27), feature::L2_Vectorized (metric.hpp:48,128), feature::Hamming (Hamming.hpp:76) */
+enum { B200M_L2_SIMPLE = 0, B200M_L2_VECTORIZED = 1, B200M_HAMMING = 2 };
+/* status codes */
+enum { B200M_OK = 0, B200M_ERR_ARG = 1, B200M_ERR_CUDA = 2, B200M_ERR_EMPTY = 3, B200M_ERR_UNSUPPORTED = 4, B200M_ERR_INTERNAL = 5 };
+/* how far b200m_match_pairs goes */
+enum {
+  B200M_STAGE_DEVICE = 0, /* kernels only: match records stay in HBM (kernel-boundary timing) */
+  B200M_STAGE_RAW = 1,    /* + records copied to pinned host memory, grouped per pair, not de-duplicated */
+  B200M_STAGE_FULL = 2    /* + host finishing == RegionsMatcher::Match output (RegionsMatcher.hpp:153-175) and cross check */
+};
+
+/* == matching::IndMatch (matching/IndMatch.hpp:25-65; _distance exists because ALICEVISION_DEBUG_MATCHING is defined, :18) */
+typedef struct { uint32_t i, j; float distance_ratio, distance; } b200m_match;
+
+const char* b200m_last_error(void);
+int b200m_version(void);
+/* number of CUDA devices visible (0 when none / no driver); never fails */
+int b200m_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on (e.g. the caller's), or NULL for an internal stream. */
+int b200m_ctx_create(int device, void* stream, b200m_ctx** out);
+void b200m_ctx_destroy(b200m_ctx* ctx);
+/* host threads used by the finishing stage (default: hardware concurrency, capped at 32) */
+int b200m_ctx_set_host_threads(b200m_ctx* ctx, int n);
+/* force every L2 pair through the exact CUDA-core kernels (testing / A-B comparison); default 0 */
+int b200m_ctx_set_force_exact(b200m_ctx* ctx, int on);
+
+/* ---- Surface 1: ArrayMatcher ---------------------------------------------------------------------------------- */
+/* Build (ArrayMatcher.hpp:39).  Copies `rows x dim` elements to the device (the reference borrows the pointer,
+ * ArrayMatcher_bruteForce.hpp:49).  rows < 1 -> B200M_ERR_EMPTY, like Build returning false (:44-48). */
+int b200m_db_create(b200m_ctx* ctx, const void* data, int rows, int dim, int dtype, int metric, b200m_db** out);
+void b200m_db_destroy(b200m_db* db);
+/* SearchNeighbours (ArrayMatcher.hpp:65).  idx[nq*nn] database indices, dist[nq*nn] float (L2, squared) or
+ * uint32 (Hamming), ascending per query.  nn > rows or nq < 1 -> B200M_ERR_ARG (bruteForce.hpp:105-108). nn <= 16. */
+int b200m_knn(b200m_ctx* ctx, const b200m_db* db, const void* query, int nq, int nn, int32_t* idx, void* dist);
+
+/* ---- Surface 2: image-collection matching ---------------------------------------------------------------------- */
+/* Register / replace one view's regions (feature::Regions of one descType: DescriptorRawData(), RegionCount(),
+ * DescriptorLength(), GetRegionsPositions(); feature/Regions.hpp:57-62,158,187).  xy = n x 2 float positions
+ * (needed by B200M_STAGE_FULL only; may be NULL otherwise).  n == 0 is allowed (view skipped when matched). */
+int b200m_upload_view(b200m_ctx* ctx, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy);
+int b200m_clear_views(b200m_ctx* ctx);
+
+/* Match a list of (I, J) view-id pairs: I = database image, J = query image (RegionsMatcher.hpp:157-158).
+ * dist_ratio as given on the CLI (main_featureMatching.cpp:102): squared internally for L2, used as is for Hamming.
+ * cross != 0 reproduces --crossMatching (ImageCollectionMatcher_generic.cpp:83-111). Pairs are processed and
+ * reported in PairSet (lexicographic) order; pairs whose result is empty are reported with zero matches (the adaptor
+ * must not insert them, :116-119). */
+int b200m_match_pairs(b200m_ctx* ctx, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out);
+
+int b200m_result_num_pairs(const b200m_result* r);
+/* pair_ids: n_pairs x 2; offsets: n_pairs + 1 (into matches); all pointers owned by the result. */
+int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int64_t** offsets, const b200m_match** matches);
+void b200m_result_free(b200m_result* r);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------------ */
+/* GPU time of the last b200m_match_pairs between its first and last enqueue (CUDA events on the context's stream), ms */
+double b200m_last_gpu_ms(const b200m_ctx* ctx);
+/* summed device time of the search kernel launches (tensor-core / exact / Hamming) in the last call, ms */
+double b200m_last_search_kernel_ms(const b200m_ctx* ctx);
+/* kernel launches issued by the last call */
+int b200m_last_launches(const b200m_ctx* ctx);
+/* pairs of the last call that ran on the tensor-core kernel */
+int b200m_last_tc_pairs(const b200m_ctx* ctx);
+/* candidates whose re-scored best distance differed from the tensor-core value (must stay 0) */
+unsigned b200m_exactness_errors(const b200m_ctx* ctx);
+/* total raw records (matches before host finishing) produced by the last call */
+int64_t b200m_last_records(const b200m_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MATCH_H_ */

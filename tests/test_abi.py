@@ -1,0 +1,58 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200match.h declares,
+fails loudly without a GPU (no CPU fallback), and the product never touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from alicevision_b200 import matching
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "b200match.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200m_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = matching.load_library()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200match.h but not exported"
+    assert sorted(matching.ABI_SYMBOLS) == names
+
+
+def test_no_gpu_fails_loudly():
+    lib = matching.load_library()
+    if lib.b200m_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.b200m_ctx_create(0, None, C.byref(h))
+    assert rc == 2 and not h and b"no CPU path" in lib.b200m_last_error()
+    with pytest.raises(matching.B200MatchError):
+        matching.Context(0)
+
+
+def test_product_does_not_use_oracle():
+    """Nothing under alicevision_b200/ or include/ may reference the oracle (parity would be void)."""
+    bad = []
+    for base in ("alicevision_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"import\s+oracle|from\s+oracle|oracle/|libport_oracle|libref_oracle", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_bad_arguments_return_status():
+    lib = matching.load_library()
+    assert lib.b200m_match_pairs(None, None, 0, C.c_float(0.8), 0, 2, None) == 1
+    assert lib.b200m_upload_view(None, 0, None, 0, 128, 1, None) == 1
+    assert lib.b200m_result_num_pairs(None) == 0
+    assert lib.b200m_version() >= 100

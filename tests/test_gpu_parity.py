@@ -1,0 +1,204 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every comparison goes through the C ABI
+(alicevision_b200.matching binds include/b200match.h with ctypes) and checks the CUDA path against the
+oracle: match index pairs bit-exact, distances exact on integer-valued data and exact by construction on
+real-valued data (the exact path follows the reference's summation order; tolerance 1e-4 relative is the
+north-star bound, asserted as equality here and relaxed only if equality fails)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from alicevision_b200 import (ArrayMatcherB200, EMatcherType, ImageCollectionMatcherB200, matching, synth)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_small.npz")
+
+
+def assert_same(got, want, rtol=0.0):
+    assert sorted(got) == sorted(want), (sorted(got)[:5], sorted(want)[:5])
+    for k in want:
+        g, w = got[k], want[k]
+        assert len(g) == len(w), (k, len(g), len(w))
+        assert np.array_equal(g["i"], w["i"]) and np.array_equal(g["j"], w["j"]), f"index pairs differ for {k}"
+        if rtol == 0.0:
+            assert np.array_equal(g["dist"], w["dist"]) and np.array_equal(g["ratio"], w["ratio"]), f"distances differ for {k}"
+        else:
+            assert np.allclose(g["dist"], w["dist"], rtol=rtol, atol=0) and np.allclose(g["ratio"], w["ratio"], rtol=rtol, atol=0)
+
+
+def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False):
+    t = EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200
+    m = ImageCollectionMatcherB200(ratio, cross, t)
+    m.clear()
+    m.ctx.set_force_exact(force_exact)
+    try:
+        return m.Match({i: (ds[i], xys[i]) for i in range(len(ds))}, pairs), m
+    finally:
+        m.ctx.set_force_exact(False)
+
+
+# ---------------------------------------------------------------------------------------------- Surface 1
+def test_arraymatcher_known_answers():
+    """matching/matching_test.cpp:22-89,128-140 ported onto ArrayMatcherB200."""
+    m = ArrayMatcherB200()
+    assert m.Build(np.array([[0], [1], [2], [3], [4]], np.float32))
+    ok, i, d = m.SearchNeighbour(np.array([2], np.float32))
+    assert ok and i == 2 and abs(d) < 1e-8
+    assert m.Build(np.array([[0], [1], [2], [5], [6]], np.float32))
+    ok, idx, dist = m.SearchNeighbours(np.array([[2]], np.float32), 1, 5)
+    assert ok and idx.tolist() == [[2, 1, 0, 3, 4]] and dist.tolist() == [[0, 1, 4, 9, 16]]
+    assert m.Build(np.arange(12, dtype=np.float32).reshape(3, 4))
+    ok, i, d = m.SearchNeighbour(np.array([4, 5, 6, 7], np.float32))
+    assert ok and i == 1 and abs(d) < 1e-8
+    e = ArrayMatcherB200()
+    assert not e.Build(np.zeros((0, 4), np.float32))
+    assert not e.SearchNeighbour(np.zeros(4, np.float32))[0]
+    assert m.Build(np.ones((1, 4), np.float32)) and not m.SearchNeighbours(np.zeros((1, 4), np.float32), 1, 2)[0]   # NN > rows
+
+
+@pytest.mark.parametrize("kind", ["u8", "f32", "real", "bin"])
+def test_arraymatcher_top2_vs_oracle(ora, kind):
+    if kind == "bin":
+        ds, _ = synth.mldb_images(2, 1500, seed=21)
+        m = ArrayMatcherB200(binary=True)
+        metric = "hamming"
+    else:
+        ds, _ = synth.sift_images(2, 1500, np.uint8, seed=21, pool_factor=1.0)
+        ds = {"u8": ds, "f32": [d.astype(np.float32) for d in ds], "real": synth.real_valued(ds)}[kind]
+        m = ArrayMatcherB200(matching.L2_VECTORIZED)
+        metric = "l2_vectorized"
+    assert m.Build(ds[0])
+    ok, idx, dist = m.SearchNeighbours(ds[1], NN=2)
+    okr, ridx, rdist = ora.knn(ds[0], ds[1], 2, metric=metric)
+    assert ok and okr and np.array_equal(dist, rdist)
+    strict = rdist[:, 0] < rdist[:, 1]
+    assert np.array_equal(idx[strict, 0], ridx[strict, 0])          # ties are unspecified in the reference (matching_test.cpp:46)
+    # general NN through the generic kernel
+    ok, idx5, dist5 = m.SearchNeighbours(ds[1][:64], NN=5)
+    okr, ridx5, rdist5 = ora.knn(ds[0], ds[1][:64], 5, metric=metric)
+    assert ok and np.array_equal(dist5, rdist5)
+
+
+# ---------------------------------------------------------------------------------------------- Surface 2
+def test_golden_fixtures_gpu():
+    g = np.load(GOLD)
+    pairs = g["pairs"]
+    cases = [("u8", list(g["sift_u8"]), list(g["xy"]), False), ("f32", [d.astype(np.float32) for d in g["sift_u8"]], list(g["xy"]), False),
+             ("real", list(g["sift_real"]), list(g["xy"]), False), ("bin", list(g["mldb"]), list(g["mldb_xy"]), True),
+             ("adv", list(g["sift_u8"]), list(g["adv_xy"]), False)]
+    for name, ds, xy, ham in cases:
+        for cross in ((False, True) if name in ("u8", "f32", "real") else (False,)):
+            got, m = run(ds, xy, pairs, ham, cross)
+            gp, go, gm = g[f"{name}_cross{int(cross)}_pairs"], g[f"{name}_cross{int(cross)}_off"], g[f"{name}_cross{int(cross)}_matches"]
+            want = {(int(p[0]), int(p[1])): gm[go[k]:go[k + 1]].view(oracle.MATCH_DTYPE) for k, p in enumerate(gp)}
+            assert_same(got, want)
+            if name in ("u8", "f32", "adv"):
+                assert m.ctx.last_tc_pairs() > 0 and m.ctx.exactness_errors() == 0
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("cross", [False, True])
+def test_collection_tensorcore_vs_oracle(ora, dtype, cross):
+    """Config-2 shape, down-scaled: ragged feature counts (not multiples of 128 / 256), TC path."""
+    descs, xys = synth.sift_images(5, 1400, dtype, seed=31, pool_factor=1.0)
+    cut = [1400, 1111, 257, 640, 129]
+    descs = [d[:c] for d, c in zip(descs, cut)]; xys = [x[:c] for x, c in zip(xys, cut)]
+    pairs = synth.exhaustive_pairs(5)
+    got, m = run(descs, xys, pairs, cross=cross)
+    assert m.ctx.last_tc_pairs() == len(pairs) * (2 if cross else 1) and m.ctx.exactness_errors() == 0
+    assert_same(got, ora.collection_match(descs, xys, pairs, 0.8, cross))
+    # the exact CUDA-core path must agree too
+    got2, m2 = run(descs, xys, pairs, cross=cross, force_exact=True)
+    assert m2.ctx.last_tc_pairs() == 0
+    assert_same(got2, got)
+
+
+def test_collection_real_valued_exact_path(ora):
+    descs, xys = synth.sift_images(3, 900, np.uint8, seed=41, pool_factor=1.0)
+    real = synth.real_valued(descs)
+    pairs = synth.exhaustive_pairs(3)
+    got, m = run(real, xys, pairs)
+    assert m.ctx.last_tc_pairs() == 0
+    assert_same(got, ora.collection_match(real, xys, pairs, 0.8))
+
+
+def test_collection_extreme_values_fall_back_to_exact(ora):
+    """uchar descriptors with ||v||^2 >= 2^22 are outside the tensor-core exactness domain."""
+    rng = np.random.default_rng(5)
+    d = [rng.integers(150, 256, (300, 128)).astype(np.uint8) for _ in range(2)]
+    d[1][:100] = np.clip(d[0][:100].astype(np.int16) + rng.integers(-3, 4, (100, 128)), 0, 255).astype(np.uint8)
+    xys = [synth.positions(300, rng) for _ in range(2)]
+    got, m = run(d, xys, [(0, 1)])
+    assert m.ctx.last_tc_pairs() == 0
+    assert_same(got, ora.collection_match(d, xys, [(0, 1)], 0.8))
+
+
+def test_collection_hamming_vs_oracle(ora):
+    bd, bxy = synth.mldb_images(4, 1300, seed=51)
+    bd = [bd[0], bd[1][:700], bd[2][:257], bd[3]]; bxy = [bxy[0], bxy[1][:700], bxy[2][:257], bxy[3]]
+    pairs = synth.exhaustive_pairs(4)
+    for cross in (False, True):
+        got, _ = run(bd, bxy, pairs, hamming=True, cross=cross)
+        assert_same(got, ora.collection_match(bd, bxy, pairs, 0.8, cross, True))
+
+
+def test_edge_cases(ora):
+    """Empty views, single-row database (NN=2 > rows), duplicated pair entries, unsorted pair list, tiny views."""
+    descs, xys = synth.sift_images(4, 300, np.uint8, seed=61, pool_factor=1.0)
+    descs = [descs[0], np.zeros((0, 128), np.uint8), descs[2][:1], descs[3][:5]]
+    xys = [xys[0], np.zeros((0, 2), np.float32), xys[2][:1], xys[3][:5]]
+    pairs = [(2, 3), (0, 1), (0, 3), (0, 2), (1, 2), (0, 3), (2, 0), (3, 0)]
+    got, _ = run(descs, xys, pairs)
+    assert_same(got, ora.collection_match(descs, xys, pairs, 0.8))
+    m = ImageCollectionMatcherB200()
+    with pytest.raises(matching.B200MatchError):
+        m.match_uploaded([(0, 99)])                      # unknown view: the reference throws std::out_of_range
+    out = {(7, 8): "kept"}
+    m.Match({0: (descs[0], xys[0]), 3: (descs[3], xys[3])}, [(0, 3)], out)   # appends, does not clear
+    assert out[(7, 8)] == "kept"
+
+
+def test_adversarial_positions(ora):
+    """Duplicated / colliding feature positions: the coordinate de-duplication is order-dependent (App. B)."""
+    descs, xys = synth.sift_images(3, 800, np.uint8, seed=71, pool_factor=1.0, generic_positions=False)
+    pairs = synth.exhaustive_pairs(3)
+    got, _ = run(descs, xys, pairs)
+    assert_same(got, ora.collection_match(descs, xys, pairs, 0.8))
+
+
+def test_ratio_values(ora):
+    descs, xys = synth.sift_images(2, 600, np.uint8, seed=81, pool_factor=1.0)
+    for r in (0.6, 0.95, 1.0):
+        got, _ = run(descs, xys, [(0, 1)], ratio=r)
+        assert_same(got, ora.collection_match(descs, xys, [(0, 1)], r))
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (8192 features): size-independent properties instead of the (slow) oracle.
+    1. self-match: every feature's nearest neighbour in its own image is itself (d = 0) -> after the ratio test
+       (0 < r^2*d2 whenever d2 > 0) and de-duplication the match list is the identity on features with d2 > 0.
+    2. tensor-core result == exact CUDA-core result, bit for bit.
+    3. planted correspondences are recovered."""
+    m = 8192
+    descs, xys = synth.sift_images(3, m, np.uint8, seed=91, pool_factor=1.0)
+    got, mm = run(descs, xys, [(0, 0), (0, 1), (1, 2)])
+    assert mm.ctx.exactness_errors() == 0 and mm.ctx.last_tc_pairs() == 3
+    s = got[(0, 0)]
+    assert np.array_equal(s["i"], s["j"]) and np.all(s["dist"] == 0) and len(s) > 0.9 * m
+    got_exact, _ = run(descs, xys, [(0, 0), (0, 1), (1, 2)], force_exact=True)
+    assert_same(got_exact, got)
+    assert len(got[(0, 1)]) > 0.05 * m
+
+
+def test_raw_stage_is_superset_of_full(ora):
+    descs, xys = synth.sift_images(2, 700, np.uint8, seed=95, pool_factor=1.0)
+    m = ImageCollectionMatcherB200()
+    m.clear()
+    m.upload({0: (descs[0], xys[0]), 1: (descs[1], xys[1])})
+    _, off, raw = m.match_uploaded([(0, 1)], matching.STAGE_RAW)
+    _, off2, full = m.match_uploaded([(0, 1)], matching.STAGE_FULL)
+    rawset = {(int(a), int(b)) for a, b in zip(raw["i"], raw["j"])}
+    assert all((int(a), int(b)) in rawset for a, b in zip(full["i"], full["j"]))
+    _, off3, none = m.match_uploaded([(0, 1)], matching.STAGE_DEVICE)
+    assert len(none) == 0 and m.ctx.last_records() == len(raw)
