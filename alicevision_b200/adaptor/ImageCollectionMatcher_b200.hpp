@@ -1,0 +1,108 @@
+// Reference-side adaptor, Surface 2: an IImageCollectionMatcher that hands the whole pair list to the B200 engine.
+// Header-only; compiled inside an AliceVision build, derives from the reference's own interface
+// (src/aliceVision/matchingImageCollection/IImageCollectionMatcher.hpp:28-42) and is the drop-in for
+// ImageCollectionMatcher_generic with BRUTE_FORCE_L2 / BRUTE_FORCE_HAMMING (ImageCollectionMatcher_generic.cpp:30-123).
+#pragma once
+
+#include <aliceVision/matchingImageCollection/IImageCollectionMatcher.hpp>
+#include <aliceVision/feature/RegionsPerView.hpp>
+
+#include <b200match.h>
+
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <typeinfo>
+#include <vector>
+
+namespace aliceVision {
+namespace matchingImageCollection {
+
+class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
+{
+  public:
+    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming = false, int device = 0)
+      : _f_dist_ratio(distRatio),
+        _useCrossMatching(crossMatching),
+        _hamming(hamming)
+    {
+        if (b200m_ctx_create(device, nullptr, &_ctx) != B200M_OK)
+            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+    }
+    ~ImageCollectionMatcher_b200() override { b200m_ctx_destroy(_ctx); }
+
+    /// Same contract as ImageCollectionMatcher_generic::Match: appends to map_PutativesMatches, never inserts empty lists,
+    /// silently skips empty / type-mismatched views (:59-63,:74-78), unknown view ids throw std::out_of_range (RegionsPerView.hpp:85).
+    void Match(std::mt19937& /*randomNumberGenerator*/,
+               const feature::RegionsPerView& regionsPerView,
+               const PairSet& pairs,
+               feature::EImageDescriberType descType,
+               matching::PairwiseMatches& map_PutativesMatches) const override
+    {
+        std::set<IndexT> used;
+        for (const Pair& p : pairs)
+        {
+            used.insert(p.first);
+            used.insert(p.second);
+        }
+        std::vector<float> xy;
+        for (IndexT viewId : used)
+        {
+            const feature::Regions& r = regionsPerView.getRegions(viewId, descType);   // throws like the reference on unknown ids
+            const int n = static_cast<int>(r.RegionCount());
+            int dtype;
+            if (r.IsBinary())
+                dtype = B200M_BIN;
+            else if (r.Type_id() == typeid(float).name())
+                dtype = B200M_F32;
+            else if (r.Type_id() == typeid(unsigned char).name())
+                dtype = B200M_U8;
+            else
+                continue;   // createRegionsMatcher has no brute-force case for other scalar types on this engine
+            xy.resize(2 * static_cast<size_t>(n));
+            const auto& feats = r.Features();
+            for (int k = 0; k < n; ++k)
+            {
+                xy[2 * k] = feats[k].x();
+                xy[2 * k + 1] = feats[k].y();
+            }
+            if (b200m_upload_view(_ctx, viewId, n ? r.DescriptorRawData() : nullptr, n, static_cast<int>(r.DescriptorLength()), dtype, xy.data()) != B200M_OK)
+                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+        }
+        std::vector<uint32_t> flat;
+        flat.reserve(2 * pairs.size());
+        for (const Pair& p : pairs)
+        {
+            flat.push_back(p.first);
+            flat.push_back(p.second);
+        }
+        b200m_result* res = nullptr;
+        if (b200m_match_pairs(_ctx, flat.data(), static_cast<int>(pairs.size()), _f_dist_ratio, _useCrossMatching ? 1 : 0, B200M_STAGE_FULL, &res) != B200M_OK)
+            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+        const uint32_t* ids = nullptr;
+        const int64_t* off = nullptr;
+        const b200m_match* m = nullptr;
+        b200m_result_get(res, &ids, &off, &m);
+        const int n = b200m_result_num_pairs(res);
+        for (int k = 0; k < n; ++k)
+        {
+            if (off[k + 1] == off[k])
+                continue;   // :116-119: empty results are not inserted
+            matching::IndMatches v;
+            v.reserve(static_cast<size_t>(off[k + 1] - off[k]));
+            for (int64_t e = off[k]; e < off[k + 1]; ++e)
+                v.emplace_back(m[e].i, m[e].j, m[e].distance_ratio, m[e].distance);
+            map_PutativesMatches[std::make_pair(ids[2 * k], ids[2 * k + 1])].emplace(descType, std::move(v));
+        }
+        b200m_result_free(res);
+    }
+
+  private:
+    float _f_dist_ratio;
+    bool _useCrossMatching;
+    bool _hamming;
+    b200m_ctx* _ctx = nullptr;
+};
+
+}  // namespace matchingImageCollection
+}  // namespace aliceVision

@@ -30,6 +30,9 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir("/root/reference/src")
     targets = ["all"] + (["ref"] if ref else [])
     subprocess.run(["make", "-C", _HERE] + targets, check=True, stdout=subprocess.DEVNULL)
+    # the C++ adaptor test needs the reference's interface headers AND the built CUDA library
+    if ref and os.path.exists(os.path.join(os.path.dirname(_HERE), "alicevision_b200", "libb200match.so")):
+        subprocess.run(["make", "-C", _HERE, "adaptor"], check=True, stdout=subprocess.DEVNULL)
 
 
 def available(kind: str) -> bool:

@@ -1,0 +1,144 @@
+// Compiles the C++ adaptors against the REFERENCE's own interface headers (through oracle/shim) and checks, on a GPU,
+// that ArrayMatcher_b200 / ImageCollectionMatcher_b200 return exactly what the reference classes return on the same
+// Regions.  Built by oracle/Makefile target `adaptor` into oracle/_ref/adaptor_test (needs /root/reference at build time).
+#include <aliceVision/matching/ArrayMatcher_bruteForce.hpp>
+#include <aliceVision/matching/RegionsMatcher.hpp>
+#include <aliceVision/feature/regionsFactory.hpp>
+
+#include <ArrayMatcher_b200.hpp>
+#include <ImageCollectionMatcher_b200.hpp>
+
+#include <cstdio>
+#include <random>
+
+using namespace aliceVision;
+using namespace aliceVision::matching;
+using namespace aliceVision::feature;
+
+static int g_fail = 0;
+#define CHECK(c)                                                     \
+    do                                                               \
+    {                                                                \
+        if (!(c))                                                    \
+        {                                                            \
+            std::printf("CHECK FAILED %s:%d  %s\n", __FILE__, __LINE__, #c); \
+            ++g_fail;                                                \
+        }                                                            \
+    } while (0)
+
+template<class RegionsT, class T>
+RegionsT* makeRegions(int n, unsigned seed, int lo, int hi, const RegionsT* plantFrom)
+{
+    std::mt19937 g(seed);
+    auto* r = new RegionsT();
+    std::vector<int> px(n), py(n);
+    for (int i = 0; i < n; ++i) { px[i] = i; py[i] = i; }
+    std::shuffle(px.begin(), px.end(), g);
+    std::shuffle(py.begin(), py.end(), g);
+    for (int i = 0; i < n; ++i)
+    {
+        r->Features().emplace_back(px[i] + 0.25f, py[i] + 0.5f, 1.f, 0.f);
+        typename RegionsT::DescriptorT d;
+        for (int k = 0; k < (int)RegionsT::DescriptorT::static_size; ++k)
+        {
+            int v = lo + int(g() % unsigned(hi - lo + 1));
+            if (plantFrom && i < n / 3)
+                v = std::min(hi, std::max(lo, int((*plantFrom).Descriptors()[i * 2 % n][k]) + int(g() % 5) - 2));
+            d[k] = T(v);
+        }
+        r->Descriptors().push_back(d);
+    }
+    return r;
+}
+
+int main()
+{
+    if (b200m_device_count() < 1)
+    {
+        std::printf("SKIP: no CUDA device\n");
+        return 0;
+    }
+    std::mt19937 rng;
+    // --- matching_test.cpp:40-71 on the adaptor (default metric L2_Simple)
+    {
+        const float array[] = {0, 1, 2, 5, 6};
+        ArrayMatcher_b200<float> m;
+        CHECK(m.Build(rng, array, 5, 1));
+        const float query[] = {2};
+        IndMatches idx; std::vector<float> d;
+        CHECK(m.SearchNeighbours(query, 1, &idx, &d, 5));
+        CHECK(idx.size() == 5 && d.size() == 5);
+        const float wantD[] = {0, 1, 4, 9, 16}; const unsigned wantI[] = {2, 1, 0, 3, 4};
+        for (int k = 0; k < 5; ++k) CHECK(d[k] == wantD[k] && idx[k]._i == 0 && idx[k]._j == wantI[k]);
+        int ni = -1; float fd = -1;
+        CHECK(m.SearchNeighbour(query, &ni, &fd) && ni == 2 && fd == 0.f);
+        ArrayMatcher_b200<float> e;
+        CHECK(!e.Build(rng, array, 0, 4));
+        CHECK(!e.SearchNeighbour(query, &ni, &fd));
+    }
+    // --- raw top-2: adaptor vs ArrayMatcher_bruteForce on SIFT-like uchar and float
+    SIFT_Regions* a = makeRegions<SIFT_Regions, unsigned char>(1500, 1, 0, 90, nullptr);
+    SIFT_Regions* b = makeRegions<SIFT_Regions, unsigned char>(1300, 2, 0, 90, a);
+    {
+        typedef L2_Vectorized<unsigned char> M;
+        ArrayMatcher_bruteForce<unsigned char, M> ref; ArrayMatcher_b200<unsigned char, M> gpu;
+        const unsigned char* A = reinterpret_cast<const unsigned char*>(a->DescriptorRawData());
+        const unsigned char* B = reinterpret_cast<const unsigned char*>(b->DescriptorRawData());
+        CHECK(ref.Build(rng, A, 1500, 128) && gpu.Build(rng, A, 1500, 128));
+        IndMatches ir, ig; std::vector<float> dr, dg;
+        CHECK(ref.SearchNeighbours(B, 1300, &ir, &dr, 2) && gpu.SearchNeighbours(B, 1300, &ig, &dg, 2));
+        CHECK(dr == dg);
+        for (size_t q = 0; q < 1300; ++q)
+            if (dr[2 * q] < dr[2 * q + 1]) CHECK(ir[2 * q]._j == ig[2 * q]._j);
+    }
+    // --- full collection Match: adaptor vs RegionsMatcher (reference) incl. cross matching
+    SIFT_Regions* c = makeRegions<SIFT_Regions, unsigned char>(900, 3, 0, 90, a);
+    RegionsPerView rpv;
+    rpv.addRegions(10, EImageDescriberType::SIFT, a);
+    rpv.addRegions(11, EImageDescriberType::SIFT, b);
+    rpv.addRegions(12, EImageDescriberType::SIFT, c);
+    rpv.addRegions(13, EImageDescriberType::SIFT, new SIFT_Regions());
+    PairSet pairs = {{10, 11}, {10, 12}, {11, 12}, {10, 13}};
+    for (int cross = 0; cross < 2; ++cross)
+    {
+        matchingImageCollection::ImageCollectionMatcher_b200 gpu(0.8f, cross != 0);
+        PairwiseMatches got;
+        gpu.Match(rng, rpv, pairs, EImageDescriberType::SIFT, got);
+        PairwiseMatches want;
+        for (const Pair& p : pairs)
+        {
+            const Regions& ri = rpv.getRegions(p.first, EImageDescriberType::SIFT);
+            const Regions& rj = rpv.getRegions(p.second, EImageDescriberType::SIFT);
+            if (ri.RegionCount() == 0 || rj.RegionCount() == 0) continue;
+            typedef ArrayMatcher_bruteForce<unsigned char, L2_Vectorized<unsigned char>> MatcherT;
+            RegionsMatcher<MatcherT> fw(rng, ri, true);
+            IndMatches v; fw.Match(0.8f, rj, v);
+            if (cross)
+            {
+                RegionsMatcher<MatcherT> bw(rng, rj, true);
+                IndMatches vc; bw.Match(0.8f, ri, vc);
+                std::set<std::pair<IndexT, IndexT>> chk;
+                for (auto& m : vc) chk.insert({m._i, m._j});
+                IndMatches kept;
+                for (auto& m : v) if (chk.count({m._j, m._i})) kept.push_back(m);
+                v.swap(kept);
+            }
+            if (!v.empty()) want[p].emplace(EImageDescriberType::SIFT, v);
+        }
+        CHECK(got.size() == want.size());
+        for (auto& kv : want)
+        {
+            auto it = got.find(kv.first);
+            CHECK(it != got.end());
+            if (it == got.end()) continue;
+            const IndMatches& w = kv.second.at(EImageDescriberType::SIFT);
+            const IndMatches& g = it->second.at(EImageDescriberType::SIFT);
+            CHECK(w.size() == g.size());
+            for (size_t k = 0; k < std::min(w.size(), g.size()); ++k)
+                CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j && w[k]._distanceRatio == g[k]._distanceRatio && w[k]._distance == g[k]._distance);
+        }
+        std::printf("collection cross=%d: %zu pairs compared\n", cross, want.size());
+    }
+    std::printf(g_fail ? "ADAPTOR TEST FAILED (%d)\n" : "ADAPTOR TEST PASSED\n", g_fail);
+    return g_fail ? 1 : 0;
+}

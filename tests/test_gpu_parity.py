@@ -202,3 +202,14 @@ def test_raw_stage_is_superset_of_full(ora):
     assert all((int(a), int(b)) in rawset for a, b in zip(full["i"], full["j"]))
     _, off3, none = m.match_uploaded([(0, 1)], matching.STAGE_DEVICE)
     assert len(none) == 0 and m.ctx.last_records() == len(raw)
+
+
+def test_cpp_adaptors_against_reference_classes():
+    """oracle/_ref/adaptor_test: the header-only C++ adaptors (deriving from the reference's ArrayMatcher /
+    IImageCollectionMatcher) vs the reference classes themselves, compiled together in the build container."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "adaptor_test")
+    if not os.path.exists(exe):
+        pytest.skip("adaptor_test not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ADAPTOR TEST PASSED" in r.stdout, r.stdout + r.stderr

@@ -1,0 +1,63 @@
+"""CPU test of the N>1 host logic: two gloo ranks shard the pair list exactly as bench.py does under torchrun,
+and the union of the shards is the whole list, disjoint and balanced, with no data-path collective needed."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_img, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    from alicevision_b200 import synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pairs = synth.exhaustive_pairs(n_img)
+    mine = bench.shard_pairs(pairs, rank, world)
+    # what bench.py reduces: max of per-rank times, sum of per-rank pair counts
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    n = torch.tensor([float(len(mine))], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    q.put((rank, mine.tolist(), t.item(), n.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_two_ranks_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_img, world = 23, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_img, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = {r: set(map(tuple, m)) for r, m, _, _ in got}
+    total = n_img * (n_img - 1) // 2
+    assert shards[0].isdisjoint(shards[1]) and len(shards[0] | shards[1]) == total
+    assert abs(len(shards[0]) - len(shards[1])) <= n_img          # balanced within one row
+    assert all(t == 2.0 and n == total for _, _, t, n in got)     # MAX / SUM reductions
+    # every database image (first index) lives on exactly one rank -> its descriptors are reused from L2
+    for r in (0, 1):
+        assert {i for i, _ in shards[r]}.isdisjoint({i for i, _ in shards[1 - r]})
+
+
+def test_shard_sizes_weak_scaling_table():
+    sys.path.insert(0, ROOT)
+    import bench
+    from alicevision_b200 import synth
+    for world, n_img in bench.IMAGES_FOR_GPUS.items():
+        pairs = synth.exhaustive_pairs(n_img)
+        sizes = [len(bench.shard_pairs(pairs, r, world)) for r in range(world)]
+        assert sum(sizes) == len(pairs)
+        assert max(sizes) - min(sizes) <= n_img
+        assert abs(np.mean(sizes) - 4950) / 4950 < 0.02
