@@ -20,7 +20,8 @@ enum : uint32_t {
 
 // One uploaded view (image) resident in HBM.
 struct alignas(128) ViewDev {
-  CUtensorMap tmap;     // fp16 [m x 128], box {64 x 128}, SWIZZLE_128B (only when dim == 128 scalar)
+  CUtensorMap tmap128;  // fp16 [m x 128], box {64 x 128 rows}, SWIZZLE_128B (query tiles; only when dim == 128 scalar)
+  CUtensorMap tmap256;  // same tensor, box {64 x 256 rows}: one box = one K-half of a database tile
   const void* raw;      // original descriptors, row-major m x dim (f32 / u8 / 64-byte binary)
   const __half* h16;    // fp16 copy (scalar, dim == 128) or nullptr
   const float* nbh;     // ||row||^2 / 2, padded to a multiple of 256 rows with 1e30f

@@ -10,6 +10,7 @@
 #include "hamming.cuh"
 #include "l2_exact.cuh"
 #include "l2_tc.cuh"
+#include "l2_tc2.cuh"
 #include "prep.cuh"
 #include "verify.cuh"
 
@@ -122,10 +123,13 @@ struct b200m_ctx {
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
   unsigned int* d_err = nullptr;
+  long long* d_trace = nullptr;   // optional pipeline trace of CTA 0 (debug)
+  int dbg_ablate = 0;             // debug-only ablation switch of the CTA-pair kernel (results are WRONG when non-zero)
   std::vector<cudaEvent_t> tev;   // search-kernel timing events, reused across calls
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   std::unique_ptr<Pool> pool;
   bool force_exact = false;
+  int tc_variant = 2;             // 1 = single-CTA kernel (l2_tc.cuh), 2 / 3 = CTA-pair kernel (l2_tc2.cuh) with 8 / 16 epilogue warps
   // last-call instrumentation
   double last_gpu_ms = 0, last_search_ms = 0; int last_launches = 0, last_tc_pairs = 0; int64_t last_records = 0;
   unsigned err_total = 0;
@@ -165,11 +169,14 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   if (v.tc_capable()) {
     const cuuint64_t gdim[2] = {128, (cuuint64_t)v.m};
     const cuuint64_t gstr[1] = {256};
-    const cuuint32_t box[2] = {64, 128};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = c->encode(&d.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.h16, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    for (int which = 0; which < 2; ++which) {
+      const cuuint32_t box[2] = {64, which ? 256u : 128u};
+      CUresult r = c->encode(which ? &d.tmap256 : &d.tmap128, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.h16, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    }
   }
   return B200M_OK;
 }
@@ -226,6 +233,8 @@ static int ensure_batch_buffers(b200m_ctx* c) {
     CK(cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming));
   }
   CK(cudaFuncSetAttribute(tc::l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
@@ -365,6 +374,24 @@ void b200m_ctx_destroy(b200m_ctx* c) {
 int b200m_ctx_set_host_threads(b200m_ctx* c, int n) {
   if (!c || n < 1) return fail(B200M_ERR_ARG, "bad arguments");
   c->pool->resize(std::min(n, 256));
+  return B200M_OK;
+}
+int b200m_ctx_set_tc_variant(b200m_ctx* c, int variant) {
+  if (!c || variant < 1 || variant > 3) return fail(B200M_ERR_ARG, "tc variant must be 1 (single CTA), 2 (CTA pair, 8 epilogue warps) or 3 (CTA pair, 16 epilogue warps)");
+  c->tc_variant = variant;
+  return B200M_OK;
+}
+// Debug: enable (n>0) / read back the per-tile pipeline trace of CTA 0 of the tensor-core kernel.
+// out receives 4 roles x TRACE_TILES x 4 SM-clock stamps (producer, MMA issuer, epilogue half 0, epilogue half 1).
+int b200m_debug_trace(b200m_ctx* c, int enable, long long* out, int n) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  c->dbg_ablate = enable >> 8;   // bits 8+: ablation mode of the CTA-pair kernel (debug only)
+  enable &= 0xff;
+  CK(cudaSetDevice(c->device));
+  const size_t total = 4ull * ptx::TRACE_TILES * 4;
+  if (enable && !c->d_trace) { CK(cudaMalloc((void**)&c->d_trace, total * 8)); CK(cudaMemset(c->d_trace, 0, total * 8)); }
+  if (out && c->d_trace) { CK(cudaStreamSynchronize(c->stream)); CK(cudaMemcpy(out, c->d_trace, std::min<size_t>(total, (size_t)n) * 8, cudaMemcpyDeviceToHost)); }
+  if (!enable && c->d_trace) { cudaFree(c->d_trace); c->d_trace = nullptr; }
   return B200M_OK;
 }
 int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
@@ -515,7 +542,8 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
       bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, d.mode};
       cbase += (uint32_t)vj.m;
-      if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + tc::BM - 1) / tc::BM; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
+      const int qrows = c->tc_variant >= 2 ? 2 * tc2::BM : tc::BM;   // queries per work item
+      if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + qrows - 1) / qrows; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
       if (d.mode == PM_EXACT_F32) { any_f32 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_EXACT_U8) { any_u8 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_HAMMING) { any_ham = true; max_qblk_ham = std::max(max_qblk_ham, (vj.m + HM_TQ - 1) / HM_TQ); }
@@ -525,9 +553,16 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     CK(cudaMemsetAsync(bb.d_count, 0, sizeof(int) * np, c->stream));
     cudaEvent_t k0 = timing_event(c, tev_used), k1 = timing_event(c, tev_used);
     CK(cudaEventRecord(k0, c->stream));
-    if (n_items) {
+    if (n_items && c->tc_variant >= 2) {
+      const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
+      if (c->tc_variant == 3)
+        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate);
+      else
+        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate);
+      ++launches;
+    } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);
-      tc::l2_top2_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq);
+      tc::l2_top2_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace);
       ++launches;
     }
     if (any_f32) {

@@ -11,18 +11,23 @@
 //   ||a-b||^2 = ||a||^2 + 2*h,   h = ||b||^2/2 - a.b
 //
 // The accumulator holds -a.b (B negated by the instruction descriptor); the epilogue adds the database
-// half-norm (one FADD per element), reduces 16-column chunks with 3-input min trees, and keeps the two
-// smallest CHUNK MINIMA plus the chunk id of the best per query row.  That is ~0.8 ALU op per element
+// half-norm (packed FADD2), reduces 16-column chunks with 3-input min trees (FMNMX3), and keeps the two
+// smallest CHUNK MINIMA plus the chunk id of the best per query row.  That is < 1 ALU op per element
 // instead of ~3 for an element-wise top-2; the price is that the second value is only an upper bound
 // when best and second-best share a chunk, which the exactness pass (verify.cuh) repairs by re-scoring
 // the 16 rows of the winning chunk for the few queries that pass the pre-test.
 //
 // CTA = 12 warps, 1 CTA/SM, persistent over work items (128 queries x whole database image):
-//   warp 0  TMA producer   Q tile (128x128 fp16, once per item) + DB tiles (256x128 fp16) + DB half-norms
+//   warp 0  TMA producer   Q tile (128x128 fp16, once per item); DB tiles (256 rows) as two K-halves of
+//                          256x64 fp16 = 32 KB, ONE TMA box each, through a 4-slot ring (a slot is refilled as soon
+//                          as the four MMAs that read it retire -> 1.5 tiles of latency tolerance)
 //   warp 1  MMA issuer     8 x tcgen05.mma.kind::f16 M128 N256 K16 per DB tile into one of 2 TMEM stages
 //   warp 2  TMEM allocator (512 columns)
+//   warp 3  half-norm producer (cp.async.bulk of 256 floats per tile, 4-slot ring)
 //   warps 4-11 epilogue    warp w reads TMEM lanes 32*(w%4).., columns 128*((w-4)/4).. of the stage
-// Pipelines: q_full/q_empty (2), db_full/db_empty (2 smem stages), tmem_full/tmem_empty + nb_full (2 TMEM stages).
+// Measured pipeline behaviour that shaped this layout (tools/gpu_trace.py, profiles/): issuing one TMA costs the
+// producer thread ~100-150 cycles regardless of size and the data lands ~600 cycles later, so few large boxes
+// and early slot release matter more than bandwidth.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -34,18 +39,20 @@ constexpr int BM = 128;            // queries per work item  (UMMA M, TMEM lanes
 constexpr int BN = 256;            // database rows per tile (UMMA N, TMEM columns per stage)
 constexpr int KD = 128;            // descriptor length
 constexpr int CHUNK = 16;          // columns per chunk minimum
-constexpr int Q_BYTES = BM * KD * 2;
-constexpr int DB_BYTES = BN * KD * 2;
+constexpr int NS = 4;              // database ring slots (each = one K-half of a tile: 256 rows x 64 fp16)
+constexpr int NBS = 4;             // half-norm ring slots
+constexpr int Q_BYTES = BM * KD * 2;        // 32 KB
+constexpr int SLOT_BYTES = BN * 64 * 2;     // 32 KB
 constexpr int NB_BYTES = BN * 4;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 
 constexpr int OFF_Q = 0;
 constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
-constexpr int OFF_NB = OFF_DB + 2 * DB_BYTES;
-constexpr int OFF_MRG = OFF_NB + 2 * NB_BYTES;        // 2 x 128 x float4
+constexpr int OFF_NB = OFF_DB + NS * SLOT_BYTES;
+constexpr int OFF_MRG = OFF_NB + NBS * NB_BYTES;      // 2 x 128 x float4
 constexpr int OFF_BAR = OFF_MRG + 2 * BM * 16;
-constexpr int NUM_BARS = 14;
+constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NBS + NBS;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -64,19 +71,31 @@ __device__ __forceinline__ void fold_chunk(const float* h, uint32_t gid, Top2& s
   s.m1 = fminf(s.m1, cm);
 }
 
+// h[0..31] = accumulator columns + database half-norms, two columns per FADD2.
+__device__ __forceinline__ void add_halfnorms(const uint32_t (&acc)[32], const float4* __restrict__ nb4, float (&h)[32]) {
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 nb = nb4[v];
+    ptx::add_f32x2(h[4 * v + 0], h[4 * v + 1], __uint_as_float(acc[4 * v + 0]), __uint_as_float(acc[4 * v + 1]), nb.x, nb.y);
+    ptx::add_f32x2(h[4 * v + 2], h[4 * v + 3], __uint_as_float(acc[4 * v + 2]), __uint_as_float(acc[4 * v + 3]), nb.z, nb.w);
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
-                  Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
+                  Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf) {
+  long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B operand tiles need 1024-B alignment
   if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars + 0;      // [2]
-  uint64_t* q_empty = bars + 2;     // [2]
-  uint64_t* db_full = bars + 4;     // [2]
-  uint64_t* db_empty = bars + 6;    // [2]
-  uint64_t* tm_full = bars + 8;     // [2]
-  uint64_t* tm_empty = bars + 10;   // [2]
-  uint64_t* nb_full = bars + 12;    // [2]
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = q_full + 2;          // [2]
+  uint64_t* db_full = q_empty + 2;         // [NS]
+  uint64_t* db_empty = db_full + NS;       // [NS]
+  uint64_t* tm_full = db_empty + NS;       // [2]
+  uint64_t* tm_empty = tm_full + 2;        // [2], 8 arrivals
+  uint64_t* nb_full = tm_empty + 2;        // [NBS]
+  uint64_t* nb_empty = nb_full + NBS;      // [NBS], 8 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
@@ -85,10 +104,10 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
-      ptx::mbar_init(&db_full[i], 1); ptx::mbar_init(&db_empty[i], 1);
       ptx::mbar_init(&tm_full[i], 1); ptx::mbar_init(&tm_empty[i], EPI_THREADS / 32);
-      ptx::mbar_init(&nb_full[i], 1);
     }
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(&db_full[i], 1); ptx::mbar_init(&db_empty[i], 1); }
+    for (int i = 0; i < NBS; ++i) { ptx::mbar_init(&nb_full[i], 1); ptx::mbar_init(&nb_empty[i], EPI_THREADS / 32); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -101,9 +120,9 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer: Q tiles and database K-halves
     if (lane == 0) {
-      uint32_t qb = 0, qph = 0, st = 0, sph = 0, ac = 0, aph = 0;
+      uint32_t qb = 0, qph = 0, st = 0, sph = 0, tt = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
         const PairDev p = pairs[w.pair];
@@ -112,23 +131,37 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
         ptx::mbar_wait(&q_empty[qb], qph ^ 1);
         ptx::mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
         uint8_t* qs = smem + OFF_Q + qb * Q_BYTES;
-        ptx::tma_load_2d(qs, &vj->tmap, &q_full[qb], 0, (int)w.qtile * BM);
-        ptx::tma_load_2d(qs + BM * 128, &vj->tmap, &q_full[qb], 64, (int)w.qtile * BM);
+        ptx::tma_load_2d(qs, &vj->tmap128, &q_full[qb], 0, (int)w.qtile * BM);
+        ptx::tma_load_2d(qs + BM * 128, &vj->tmap128, &q_full[qb], 64, (int)w.qtile * BM);
         qb ^= 1; if (qb == 0) qph ^= 1;
         const int ntiles = ((int)p.m_i + BN - 1) / BN;
         for (int t = 0; t < ntiles; ++t) {
-          ptx::mbar_wait(&db_empty[st], sph ^ 1);
-          ptx::mbar_wait(&tm_empty[ac], aph ^ 1);          // nb[ac] is free once the epilogue released TMEM stage ac
-          uint8_t* ds = smem + OFF_DB + st * DB_BYTES;
-          ptx::mbar_arrive_expect_tx(&db_full[st], DB_BYTES);
-          ptx::tma_load_2d(ds, &vi->tmap, &db_full[st], 0, t * BN);
-          ptx::tma_load_2d(ds + 128 * 128, &vi->tmap, &db_full[st], 0, t * BN + 128);
-          ptx::tma_load_2d(ds + BN * 128, &vi->tmap, &db_full[st], 64, t * BN);
-          ptx::tma_load_2d(ds + BN * 128 + 128 * 128, &vi->tmap, &db_full[st], 64, t * BN + 128);
-          ptx::mbar_arrive_expect_tx(&nb_full[ac], NB_BYTES);
-          ptx::bulk_load_1d(smem + OFF_NB + ac * NB_BYTES, vi->nbh + (size_t)t * BN, NB_BYTES, &nb_full[ac]);
-          st ^= 1; if (st == 0) sph ^= 1;
-          ac ^= 1; if (ac == 0) aph ^= 1;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            ptx::mbar_wait(&db_empty[st], sph ^ 1);
+            if (kb == 0) ptx::trace_stamp(trace, 0, tt, 0);
+            ptx::mbar_arrive_expect_tx(&db_full[st], SLOT_BYTES);
+            ptx::tma_load_2d(smem + OFF_DB + st * SLOT_BYTES, &vi->tmap256, &db_full[st], kb * 64, t * BN);
+            if (++st == NS) { st = 0; sph ^= 1; }
+          }
+          ptx::trace_stamp(trace, 0, tt, 1); ++tt;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ half-norm producer
+    if (lane == 0) {
+      uint32_t ns = 0, nph = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem w = items[it];
+        const PairDev p = pairs[w.pair];
+        const float* nbh = views[p.view_i].nbh;
+        const int ntiles = ((int)p.m_i + BN - 1) / BN;
+        for (int t = 0; t < ntiles; ++t) {
+          ptx::mbar_wait(&nb_empty[ns], nph ^ 1);
+          ptx::mbar_arrive_expect_tx(&nb_full[ns], NB_BYTES);
+          ptx::bulk_load_1d(smem + OFF_NB + ns * NB_BYTES, nbh + (size_t)t * BN, NB_BYTES, &nb_full[ns]);
+          if (++ns == NBS) { ns = 0; nph ^= 1; }
         }
       }
     }
@@ -138,25 +171,33 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
       constexpr uint32_t idesc = ptx::umma_idesc_f16(BM, BN, false, true);   // D = A * (-B)^T
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t db_addr = ptx::smem_u32(smem + OFF_DB);
-      uint32_t qb = 0, qph = 0, st = 0, sph = 0, ac = 0, aph = 0;
+      uint32_t qb = 0, qph = 0, st = 0, sph = 0, ac = 0, aph = 0, tt = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const WorkItem w = items[it];
         const PairDev p = pairs[w.pair];
         const int ntiles = ((int)p.m_i + BN - 1) / BN;
         ptx::mbar_wait(&q_full[qb], qph);
         for (int t = 0; t < ntiles; ++t) {
-          ptx::mbar_wait(&db_full[st], sph);
-          ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
-          ptx::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < KD / 16; ++k) {
-            const uint64_t ad = ptx::umma_desc_k_sw128(q_addr + qb * Q_BYTES + (k >> 2) * (BM * 128) + (k & 3) * 32);
-            const uint64_t bd = ptx::umma_desc_k_sw128(db_addr + st * DB_BYTES + (k >> 2) * (BN * 128) + (k & 3) * 32);
-            ptx::umma_f16_ss(tmem_base + ac * BN, ad, bd, idesc, k > 0 ? 1u : 0u);
+          for (int kb = 0; kb < 2; ++kb) {
+            ptx::mbar_wait(&db_full[st], sph);
+            if (kb == 0) {
+              ptx::trace_stamp(trace, 1, tt, 0);
+              ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
+              ptx::trace_stamp(trace, 1, tt, 1);
+            }
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::umma_desc_k_sw128(q_addr + qb * Q_BYTES + kb * (BM * 128) + k * 32);
+              const uint64_t bd = ptx::umma_desc_k_sw128(db_addr + st * SLOT_BYTES + k * 32);
+              ptx::umma_f16_ss(tmem_base + ac * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
+            ptx::umma_commit(&db_empty[st]);
+            if (++st == NS) { st = 0; sph ^= 1; }
           }
-          ptx::umma_commit(&db_empty[st]);
           ptx::umma_commit(&tm_full[ac]);
-          st ^= 1; if (st == 0) sph ^= 1;
+          ptx::trace_stamp(trace, 1, tt, 2); ++tt;
           ac ^= 1; if (ac == 0) aph ^= 1;
         }
         ptx::umma_commit(&q_empty[qb]);
@@ -168,18 +209,21 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int half = (warp - 4) >> 2;        // which 128 columns of the 256-column stage
     const int row = quad * 32 + lane;        // query row inside the tile
-    uint32_t ac = 0, aph = 0, par = 0;
+    uint32_t ac = 0, aph = 0, ns = 0, nph = 0, par = 0, tt = 0;
+    long long* etrace = (lane == 0 && quad == 0) ? trace : nullptr;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       const PairDev p = pairs[w.pair];
       const int ntiles = ((int)p.m_i + BN - 1) / BN;
       Top2 s{INFINITY, INFINITY, 0u};
       for (int t = 0; t < ntiles; ++t) {
-        ptx::mbar_wait(&nb_full[ac], aph);
+        ptx::mbar_wait(&nb_full[ns], nph);
+        ptx::trace_stamp(etrace, 2 + half, tt, 0);
         ptx::mbar_wait(&tm_full[ac], aph);
+        ptx::trace_stamp(etrace, 2 + half, tt, 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ac * BN + half * 128;
-        const float4* nb4 = reinterpret_cast<const float4*>(smem + OFF_NB + ac * NB_BYTES) + half * 32;
+        const float4* nb4 = reinterpret_cast<const float4*>(smem + OFF_NB + ns * NB_BYTES) + half * 32;
         const uint32_t gbase = (uint32_t)t * (BN / CHUNK) + half * (128 / CHUNK);
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32b_x32(taddr, ra);
@@ -190,22 +234,17 @@ l2_top2_tc_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
           uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
           if (c < 3) ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, nxt);
           float h[32];
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 nb = nb4[c * 8 + v];
-            h[4 * v + 0] = __uint_as_float(cur[4 * v + 0]) + nb.x;
-            h[4 * v + 1] = __uint_as_float(cur[4 * v + 1]) + nb.y;
-            h[4 * v + 2] = __uint_as_float(cur[4 * v + 2]) + nb.z;
-            h[4 * v + 3] = __uint_as_float(cur[4 * v + 3]) + nb.w;
-          }
+          add_halfnorms(cur, nb4 + c * 8, h);
           fold_chunk(h, gbase + c * 2, s);
           fold_chunk(h + 16, gbase + c * 2 + 1, s);
           if (c < 3) ptx::tmem_ld_wait();
         }
+        ptx::trace_stamp(etrace, 2 + half, tt, 2); ++tt;
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tm_empty[ac]);
+        if (lane == 0) { ptx::mbar_arrive(&tm_empty[ac]); ptx::mbar_arrive(&nb_empty[ns]); }
         ac ^= 1; if (ac == 0) aph ^= 1;
+        if (++ns == NBS) { ns = 0; nph ^= 1; }
       }
       // merge the two column halves of each query row, pre-test, emit candidates
       float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * BM;

@@ -1,0 +1,259 @@
+// K1 (2-CTA) — the same distance GEMM + fused top-2 as l2_tc.cuh, issued as cta_group::2 MMAs by CTA pairs.
+//
+// Why: ncu of the 1-CTA kernel (profiles/r01_ncu_l2_top2_tc_kernel.md) shows the tensor pipe 55 % busy with nothing
+// else saturated: per 1024-cycle tile one SM must read 96 KB of operands from shared memory for the MMA and accept
+// 64 KB of TMA writes (= 160 KB at 128 B/clk -> >= 1250 cycles), with only two 64 KB stages to hide the L2 latency.
+// A CTA pair executing one M=256 x N=256 x K=16 MMA halves both: each CTA stages only ITS 128 rows of the 256-row
+// database tile (32 KB per tile, 4-stage ring = 4 tiles of prefetch) and the MMA reads 64 KB per tile per SM.
+//
+// Work item = 256 consecutive queries of J (128 per CTA of the pair) x the whole database image I.
+//   every CTA : warp 0 TMA producer (own Q tile, own half of each DB tile, full 256-entry half-norm chunk),
+//               warp 2 TMEM allocator (cta_group::2), warps 4-11 epilogue on its own 128 accumulator rows
+//   leader CTA: warp 1 issues tcgen05.mma.cta_group::2; completions are multicast to both CTAs' barriers
+// Barrier homes: q_full / db_full / tm_empty live in the LEADER (TMA bytes of both CTAs and the epilogue arrivals of
+// both CTAs are credited there); q_empty / db_empty / tm_full / nb_full / nb_empty are per CTA.
+#pragma once
+#include "l2_tc.cuh"
+
+namespace b200m {
+namespace tc2 {
+
+constexpr int BM = 128;                 // queries per CTA (256 per pair)
+constexpr int BN = 256;                 // database rows per tile (128 staged per CTA)
+constexpr int NS = 4;                   // database smem stages per CTA
+constexpr int Q_BYTES = BM * 128 * 2;   // 32 KB
+constexpr int DBH_BYTES = 128 * 128 * 2;  // 32 KB: this CTA's half of a database tile
+constexpr int NB_BYTES = BN * 4;
+constexpr int MAX_EPI_WARPS = 16;
+
+constexpr int OFF_Q = 0;
+constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
+constexpr int OFF_NB = OFF_DB + NS * DBH_BYTES;
+constexpr int OFF_MRG = OFF_NB + NS * NB_BYTES;
+constexpr int OFF_BAR = OFF_MRG + 2 * 3 * BM * 16;   // double-buffered, up to 3 partial top-2 records per row
+constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS;
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+
+template <int EPI_WARPS>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
+l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
+                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg) {
+  long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;                  // [2]  leader
+  uint64_t* q_empty = q_full + 2;           // [2]  per CTA (multicast commit)
+  uint64_t* db_full = q_empty + 2;          // [NS] leader
+  uint64_t* db_empty = db_full + NS;        // [NS] per CTA (multicast commit)
+  uint64_t* tm_full = db_empty + NS;        // [2]  per CTA (multicast commit)
+  uint64_t* tm_empty = tm_full + 2;         // [2]  leader, 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint64_t* nb_full = tm_empty + 2;         // [NS] per CTA (half-norm ring, same index as the database stage)
+  uint64_t* nb_empty = nb_full + NS;        // [NS] per CTA, 8 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();      // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
+      ptx::mbar_init(&tm_full[i], 1); ptx::mbar_init(&tm_empty[i], 2 * EPI_WARPS);
+    }
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&db_full[i], 1); ptx::mbar_init(&db_empty[i], 1);
+      ptx::mbar_init(&nb_full[i], 1); ptx::mbar_init(&nb_empty[i], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  __syncwarp();                      // barrier.cluster is .aligned: every warp must reach it converged
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();          // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t qb = 0, qph = 0, st = 0, sph = 0, tt = 0;
+      for (int it = cluster_id; it < n_items; it += n_clusters) {
+        const WorkItem w = items[it];
+        const PairDev p = pairs[w.pair];
+        const ViewDev* vi = views + p.view_i;
+        const ViewDev* vj = views + p.view_j;
+        const int qrow = ((int)w.qtile * 2 + (int)rank) * BM;
+        ptx::mbar_wait(&q_empty[qb], qph ^ 1);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * Q_BYTES);
+        uint8_t* qs = smem + OFF_Q + qb * Q_BYTES;
+        ptx::tma_load_2d_2sm(qs, &vj->tmap128, &q_full[qb], 0, qrow);
+        ptx::tma_load_2d_2sm(qs + BM * 128, &vj->tmap128, &q_full[qb], 64, qrow);
+        qb ^= 1; if (qb == 0) qph ^= 1;
+        const int ntiles = ((int)p.m_i + BN - 1) / BN;
+        for (int t = 0; t < ntiles; ++t) {
+          ptx::mbar_wait(&db_empty[st], sph ^ 1);
+          ptx::mbar_wait(&nb_empty[st], sph ^ 1);         // released by the epilogue NS tiles ago: never on the critical path
+          ptx::trace_stamp(trace, 0, tt, 0);
+          uint8_t* ds = smem + OFF_DB + st * DBH_BYTES;
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&db_full[st], 2 * DBH_BYTES);
+          const int drow = t * BN + (int)rank * 128;
+          ptx::tma_load_2d_2sm(ds, &vi->tmap128, &db_full[st], 0, drow);
+          ptx::tma_load_2d_2sm(ds + 128 * 128, &vi->tmap128, &db_full[st], 64, drow);
+          ptx::mbar_arrive_expect_tx(&nb_full[st], NB_BYTES);
+          ptx::bulk_load_1d(smem + OFF_NB + st * NB_BYTES, vi->nbh + (size_t)t * BN, NB_BYTES, &nb_full[st]);
+          ptx::trace_stamp(trace, 0, tt, 1); ++tt;
+          if (++st == NS) { st = 0; sph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN, false, true);   // M=256 across the pair, D = A * (-B)^T
+      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
+      const uint32_t db_addr = ptx::smem_u32(smem + OFF_DB);
+      uint32_t qb = 0, qph = 0, st = 0, sph = 0, ac = 0, aph = 0, tt = 0;
+      for (int it = cluster_id; it < n_items; it += n_clusters) {
+        const WorkItem w = items[it];
+        const PairDev p = pairs[w.pair];
+        const int ntiles = ((int)p.m_i + BN - 1) / BN;
+        ptx::mbar_wait(&q_full[qb], qph);
+        bool db_ready = false, tm_ready = false;   // barriers of the coming tile already observed
+        for (int t = 0; t < ntiles; ++t) {
+          if (!db_ready) ptx::mbar_wait(&db_full[st], sph);
+          if (!tm_ready) ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
+          ptx::trace_stamp(trace, 1, tt, 1);
+          ptx::tc_fence_after();
+          const uint32_t a_base = q_addr + qb * Q_BYTES, b_base = db_addr + st * DBH_BYTES, d_addr = tmem_base + ac * BN;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + k * 32), ptx::umma_desc_k_sw128(b_base + k * 32), idesc, k > 0 ? 1u : 0u);
+          // While the tensor pipe chews on the first four MMAs, look at the NEXT tile's barriers: observing a completed
+          // mbarrier costs ~100 cycles, and two of them per tile between commits would idle the pipe.  The database
+          // slot is normally long since full (blocking wait is free); the TMEM stage may not be drained yet, so it is
+          // only polled once here and waited for at the top of the next tile if needed.
+          const uint32_t nst = (st + 1 == NS) ? 0 : st + 1, nsph = (st + 1 == NS) ? (sph ^ 1) : sph;
+          const uint32_t nac = ac ^ 1, naph = (nac == 0) ? (aph ^ 1) : aph;
+          db_ready = tm_ready = false;
+          if (t + 1 < ntiles) {
+            db_ready = ptx::mbar_try_wait(&db_full[nst], nsph);
+            tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+          }
+#pragma unroll
+          for (int k = 4; k < 8; ++k)
+            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + (BM * 128) + (k & 3) * 32),
+                                 ptx::umma_desc_k_sw128(b_base + (128 * 128) + (k & 3) * 32), idesc, 1u);
+          ptx::umma_commit_2sm_mc(&db_empty[st], 3);
+          ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
+          ptx::trace_stamp(trace, 1, tt, 2); ++tt;
+          st = nst; sph = nsph; ac = nac; aph = naph;
+        }
+        ptx::umma_commit_2sm_mc(&q_empty[qb], 3);
+        qb ^= 1; if (qb == 0) qph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (EPI_WARPS warps per CTA, own 128 rows)
+    constexpr int NQ = EPI_WARPS / 4;            // column groups per stage (2 or 4)
+    constexpr int COLS = BN / NQ;                // accumulator columns per warp (128 or 64)
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int colq = (warp - 4) >> 2;            // which column group
+    const int row = quad * 32 + lane;
+    uint32_t ac = 0, aph = 0, st = 0, sph = 0, par = 0, tt = 0;
+    long long* etrace = (lane == 0 && quad == 0 && colq < 2) ? trace : nullptr;
+    for (int it = cluster_id; it < n_items; it += n_clusters) {
+      const WorkItem w = items[it];
+      const PairDev p = pairs[w.pair];
+      const int ntiles = ((int)p.m_i + BN - 1) / BN;
+      tc::Top2 s{INFINITY, INFINITY, 0u};
+      for (int t = 0; t < ntiles; ++t) {
+        ptx::mbar_wait(&nb_full[st], sph);
+        ptx::trace_stamp(etrace, 2 + colq, tt, 0);
+        ptx::mbar_wait(&tm_full[ac], aph);
+        ptx::trace_stamp(etrace, 2 + colq, tt, 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ac * BN + colq * COLS;
+        const float4* nb4 = reinterpret_cast<const float4*>(smem + OFF_NB + st * NB_BYTES) + colq * (COLS / 4);
+        const uint32_t gbase = (uint32_t)t * (BN / tc::CHUNK) + colq * (COLS / tc::CHUNK);
+        uint32_t ra[32], rb[32];
+        if (dbg < 2) {
+        ptx::tmem_ld_32x32b_x32(taddr, ra);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+          uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+          if (c + 1 < COLS / 32) ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, nxt);
+          if (dbg == 0) {
+            float h[32];
+            tc::add_halfnorms(cur, nb4 + c * 8, h);
+            tc::fold_chunk(h, gbase + c * 2, s);
+            tc::fold_chunk(h + 16, gbase + c * 2 + 1, s);
+          } else {
+            float keepalive = __uint_as_float(cur[0]);
+#pragma unroll
+            for (int e = 1; e < 32; ++e) keepalive = fminf(keepalive, __uint_as_float(cur[e]));   // 31 ops: keeps the loads alive
+            s.m1 = fminf(s.m1, keepalive);
+          }
+          if (c + 1 < COLS / 32) ptx::tmem_ld_wait();
+        }
+        }
+        ptx::trace_stamp(etrace, 2 + colq, tt, 2); ++tt;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&nb_empty[st]);                // local: the half-norm buffer may be overwritten
+          ptx::mbar_arrive_cluster(&tm_empty[ac], 0);     // leader: this CTA's rows of TMEM stage ac are drained
+        }
+        ac ^= 1; if (ac == 0) aph ^= 1;
+        if (++st == NS) { st = 0; sph ^= 1; }
+      }
+      // merge the column groups of each query row, pre-test, emit candidates
+      float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * 3 * BM;
+      if (colq > 0) mrg[(colq - 1) * BM + row] = make_float4(s.m1, s.m2, __uint_as_float(s.g1), 0.f);
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      if (colq == 0) {
+        float m1 = s.m1, m2 = s.m2; uint32_t g1 = s.g1;
+#pragma unroll
+        for (int o_ = 0; o_ < NQ - 1; ++o_) {
+          const float4 o = mrg[o_ * BM + row];
+          m2 = fminf(fmaxf(m1, o.x), fminf(m2, o.y));
+          g1 = (o.x < m1) ? __float_as_uint(o.z) : g1;
+          m1 = fminf(m1, o.x);
+        }
+        const uint32_t q = (w.qtile * 2 + rank) * BM + row;
+        bool keep = false;
+        float d1 = 0.f, d2 = 0.f;
+        if (q < p.m_j) {
+          const float na = views[p.view_j].nrm[q];
+          d1 = fmaf(2.f, m1, na);
+          d2 = fmaf(2.f, m2, na);
+          keep = d1 < __fmul_rn(ratio_sq, d2);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (mask) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&cand_count[w.pair], __popc(mask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) cands[p.cand_base + base + __popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
+        }
+      }
+      par ^= 1;
+    }
+  }
+
+  __syncwarp();                      // lanes 1-31 of the single-lane role warps wait here for lane 0
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();          // the peer may still be signalling / reading this CTA's shared memory until here
+  if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
+}
+
+}  // namespace tc2
+}  // namespace b200m

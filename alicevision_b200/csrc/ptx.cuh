@@ -125,6 +125,58 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------- 2-CTA (cta_group::2) variants and cluster helpers
+// A CTA pair (cluster of 2 on one TPC) executes one M=256 MMA: each CTA supplies 128 rows of A and 128 rows of B from
+// its own shared memory (same offsets in both CTAs) and receives 128 accumulator rows in its own TMEM.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"   // default .release.cta: a cluster-scope release costs a full fence per tile
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of the pair; completion bytes are credited to the LEADER CTA's barrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Completion of all prior MMAs of this thread arrives on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread t gets lane t of the warp's quadrant).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -145,6 +197,21 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// Packed fp32x2 add (sm_100+: one FADD2 for two columns): (o0,o1) = (a0,a1) + (b0,b1), round-to-nearest like FADD.
+__device__ __forceinline__ void add_f32x2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  uint64_t x, y, z;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(z));
+}
+
+// Optional pipeline trace (debug): SM-clock timestamps of one CTA's roles, written only when `trace` is non-null.
+constexpr int TRACE_TILES = 512;
+__device__ __forceinline__ void trace_stamp(long long* trace, int role, uint32_t tile, int k) {
+  if (trace != nullptr && tile < TRACE_TILES) trace[((size_t)role * TRACE_TILES + tile) * 4 + k] = clock64();
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

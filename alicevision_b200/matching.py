@@ -30,7 +30,7 @@ MATCH_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("ratio", np.float32
 # every symbol include/b200match.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
-    "b200m_ctx_set_force_exact", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_clear_views",
+    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_clear_views",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
 ]
@@ -110,6 +110,15 @@ class Context:
 
     def set_force_exact(self, on: bool) -> None:
         _check(self.lib.b200m_ctx_set_force_exact(self._h, C.c_int(int(on))), "b200m_ctx_set_force_exact")
+
+    def set_tc_variant(self, variant: int) -> None:
+        _check(self.lib.b200m_ctx_set_tc_variant(self._h, C.c_int(variant)), "b200m_ctx_set_tc_variant")
+
+    def debug_trace(self, enable: bool = True, read: bool = False):
+        """Enable / read the per-tile pipeline trace (roles x 512 tiles x 4 stamps) of CTA 0 of the tensor-core kernel."""
+        out = np.zeros((4, 512, 4), np.int64)
+        _check(self.lib.b200m_debug_trace(self._h, C.c_int(int(enable)), out.ctypes.data_as(C.c_void_p) if read else None, C.c_int(out.size)), "b200m_debug_trace")
+        return out
 
     # instrumentation
     def last_gpu_ms(self) -> float: return self.lib.b200m_last_gpu_ms(self._h)

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--images", type=int, default=0, help="0 = 100 per GPU-equivalent (IMAGES_FOR_GPUS)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "u8", "bin"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--tc-variant", type=int, default=2, choices=[1, 2, 3], help="2/3 = CTA-pair tcgen05 kernel with 8/16 epilogue warps, 1 = single-CTA kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -179,6 +180,7 @@ def main():
     descs, xys, pairs = make_workload(args, world)
     mine = shard_pairs(pairs, rank, world)
     ctx = matching.Context(local)
+    ctx.set_tc_variant(args.tc_variant)
     m = ImageCollectionMatcherB200(0.8, False, EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200, ctx)
     views = {i: (descs[i], xys[i]) for i in range(len(descs))}
     m.upload(views)
@@ -248,7 +250,7 @@ def main():
                                "note": "popc-issue bound by construction (M^2*16 popc32 per pair vs 2*M*64 bytes); HBM fraction reported because the north star asks"}
         else:
             out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                               "kernel": "l2_top2_tc_kernel", "peak_source": peak_src, "flop_per_pair": flop_pair,
+                               "kernel": ("tc2::l2_top2_tc2_kernel<%d> (cta_group::2)" % (8 if args.tc_variant == 2 else 16)) if args.tc_variant >= 2 else "tc::l2_top2_tc_kernel", "peak_source": peak_src, "flop_per_pair": flop_pair,
                                "kernel_ms_per_step": ms_search}
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(descs, xys, pairs, hamming, args.cpu_seconds)

@@ -27,15 +27,17 @@ def assert_same(got, want, rtol=0.0):
             assert np.allclose(g["dist"], w["dist"], rtol=rtol, atol=0) and np.allclose(g["ratio"], w["ratio"], rtol=rtol, atol=0)
 
 
-def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False):
+def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False, variant=2):
     t = EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200
     m = ImageCollectionMatcherB200(ratio, cross, t)
     m.clear()
     m.ctx.set_force_exact(force_exact)
+    m.ctx.set_tc_variant(variant)
     try:
         return m.Match({i: (ds[i], xys[i]) for i in range(len(ds))}, pairs), m
     finally:
         m.ctx.set_force_exact(False)
+        m.ctx.set_tc_variant(2)
 
 
 # ---------------------------------------------------------------------------------------------- Surface 1
@@ -97,15 +99,16 @@ def test_golden_fixtures_gpu():
                 assert m.ctx.last_tc_pairs() > 0 and m.ctx.exactness_errors() == 0
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
 @pytest.mark.parametrize("cross", [False, True])
-def test_collection_tensorcore_vs_oracle(ora, dtype, cross):
+def test_collection_tensorcore_vs_oracle(ora, dtype, cross, variant):
     """Config-2 shape, down-scaled: ragged feature counts (not multiples of 128 / 256), TC path."""
     descs, xys = synth.sift_images(5, 1400, dtype, seed=31, pool_factor=1.0)
     cut = [1400, 1111, 257, 640, 129]
     descs = [d[:c] for d, c in zip(descs, cut)]; xys = [x[:c] for x, c in zip(xys, cut)]
     pairs = synth.exhaustive_pairs(5)
-    got, m = run(descs, xys, pairs, cross=cross)
+    got, m = run(descs, xys, pairs, cross=cross, variant=variant)
     assert m.ctx.last_tc_pairs() == len(pairs) * (2 if cross else 1) and m.ctx.exactness_errors() == 0
     assert_same(got, ora.collection_match(descs, xys, pairs, 0.8, cross))
     # the exact CUDA-core path must agree too
@@ -174,7 +177,8 @@ def test_ratio_values(ora):
         assert_same(got, ora.collection_match(descs, xys, [(0, 1)], r))
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_full_size_properties(variant):
     """BASELINE config sizes (8192 features): size-independent properties instead of the (slow) oracle.
     1. self-match: every feature's nearest neighbour in its own image is itself (d = 0) -> after the ratio test
        (0 < r^2*d2 whenever d2 > 0) and de-duplication the match list is the identity on features with d2 > 0.
@@ -182,7 +186,7 @@ def test_full_size_properties():
     3. planted correspondences are recovered."""
     m = 8192
     descs, xys = synth.sift_images(3, m, np.uint8, seed=91, pool_factor=1.0)
-    got, mm = run(descs, xys, [(0, 0), (0, 1), (1, 2)])
+    got, mm = run(descs, xys, [(0, 0), (0, 1), (1, 2)], variant=variant)
     assert mm.ctx.exactness_errors() == 0 and mm.ctx.last_tc_pairs() == 3
     s = got[(0, 0)]
     assert np.array_equal(s["i"], s["j"]) and np.all(s["dist"] == 0) and len(s) > 0.9 * m

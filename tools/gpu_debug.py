@@ -7,12 +7,13 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-EXPERIMENTS = ["exact_vs_oracle", "tc_small", "tc_medium", "tc_multi", "tc_big"]
+EXPERIMENTS = ["tc_small", "tc_medium", "tc_multi", "tc_big"]
 
 
-def raw(m, pairs, force_exact, stage=1):
+def raw(m, pairs, force_exact, stage=1, variant=2):
     from alicevision_b200 import matching
     m.ctx.set_force_exact(force_exact)
+    m.ctx.set_tc_variant(variant)
     pid, off, mat = m.match_uploaded(pairs, stage)
     m.ctx.set_force_exact(False)
     return {(int(pid[k, 0]), int(pid[k, 1])): mat[off[k]:off[k + 1]] for k in range(len(pid))}
@@ -56,9 +57,10 @@ def experiment(name):
     pairs = synth.exhaustive_pairs(sizes[0])
     a = raw(m, pairs, True)
     print("  exact done; launches", m.ctx.last_launches())
-    b = raw(m, pairs, False)
-    print("  tc done; tc_pairs", m.ctx.last_tc_pairs(), "exactness_errors", m.ctx.exactness_errors(), "gpu_ms", m.ctx.last_gpu_ms(), "search_ms", m.ctx.last_search_kernel_ms())
-    cmp_raw(a, b, name)
+    for variant in (1, 2):
+        b = raw(m, pairs, False, variant=variant)
+        print(f"  tc variant {variant} done; tc_pairs", m.ctx.last_tc_pairs(), "exactness_errors", m.ctx.exactness_errors(), "gpu_ms", m.ctx.last_gpu_ms(), "search_ms", m.ctx.last_search_kernel_ms(), flush=True)
+        cmp_raw(a, b, f"{name}/v{variant}")
 
 
 if __name__ == "__main__":
