@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -86,6 +87,14 @@ class Pool {
   bool quit_ = false;
 };
 
+// Completion tracking for one group of pool tasks (one batch of finishing work).
+struct TaskGroup {
+  std::mutex mu; std::condition_variable cv; int left = 0;
+  void add(int n) { std::lock_guard<std::mutex> l(mu); left += n; }
+  void done() { std::lock_guard<std::mutex> l(mu); if (--left == 0) cv.notify_all(); }
+  void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [this] { return left == 0; }); }
+};
+
 // ------------------------------------------------------------------------------------------------ data model
 struct ViewHost {
   uint32_t id = 0;
@@ -118,10 +127,14 @@ struct b200m_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   bool own_stream = false;
   EncodeTiledFn encode = nullptr;
-  std::vector<ViewHost> views;
+  std::deque<ViewHost> views;     // deque: references stay valid while pool tasks (position checks) run
   std::unordered_map<uint32_t, int> slot_of;
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
+  // upload staging: pageable caller memory -> pinned ring (parallel memcpy on the pool) -> async H2D
+  static constexpr int NSTG = 4;
+  void* stg[NSTG] = {nullptr, nullptr, nullptr, nullptr}; size_t stg_bytes[NSTG] = {0, 0, 0, 0}; cudaEvent_t stg_ev[NSTG] = {nullptr, nullptr, nullptr, nullptr}; int stg_next = 0;
+  ViewDev* h_views = nullptr;     // pinned mirror of the device view table (source of the async table updates)
   unsigned int* d_err = nullptr;
   long long* d_trace = nullptr;   // optional pipeline trace of CTA 0 (debug)
   int dbg_ablate = 0;             // debug-only ablation switch of the CTA-pair kernel (results are WRONG when non-zero)
@@ -138,15 +151,53 @@ struct b200m_ctx {
 struct b200m_db { b200m_ctx* ctx; ViewHost v; int metric; };
 
 struct b200m_result {
-  std::vector<uint32_t> pair_ids; std::vector<int64_t> offsets; std::vector<b200m_match> matches;
+  std::vector<uint32_t> pair_ids; std::vector<int64_t> offsets;
+  std::unique_ptr<b200m_match[]> matches;   // uninitialised storage: filled by parallel copies
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
+// Copies caller (pageable) memory to the device through a pinned staging ring; the host-side memcpy is split over the pool.
+static int staged_h2d(b200m_ctx* c, void* dst, const void* src, size_t bytes) {
+  size_t done = 0;
+  const size_t CH = 16u << 20;
+  while (done < bytes) {
+    const size_t n = std::min(CH, bytes - done);
+    const int sidx = c->stg_next; c->stg_next = (c->stg_next + 1) % b200m_ctx::NSTG;
+    if (c->stg_bytes[sidx] < n) {
+      if (c->stg[sidx]) { CK(cudaEventSynchronize(c->stg_ev[sidx])); CK(cudaFreeHost(c->stg[sidx])); c->stg[sidx] = nullptr; }
+      CK(cudaMallocHost(&c->stg[sidx], std::max(n, (size_t)(4u << 20))));
+      c->stg_bytes[sidx] = std::max(n, (size_t)(4u << 20));
+      if (!c->stg_ev[sidx]) CK(cudaEventCreateWithFlags(&c->stg_ev[sidx], cudaEventDisableTiming));
+    } else {
+      CK(cudaEventSynchronize(c->stg_ev[sidx]));     // the previous H2D out of this buffer has completed
+    }
+    char* d = (char*)c->stg[sidx]; const char* sp = (const char*)src + done;
+    const int parts = (int)std::min<size_t>(8, std::max<size_t>(1, n >> 19));
+    if (parts > 1) {
+      std::atomic<int> left{parts};
+      std::mutex mu; std::condition_variable cv;
+      for (int k = 0; k < parts; ++k) {
+        const size_t a = n * k / parts, b = n * (k + 1) / parts;
+        c->pool->submit([=, &left, &mu, &cv] { std::memcpy(d + a, sp + a, b - a); if (--left == 0) { std::lock_guard<std::mutex> l(mu); cv.notify_one(); } });
+      }
+      std::unique_lock<std::mutex> l(mu);
+      cv.wait(l, [&] { return left.load() == 0; });
+    } else {
+      std::memcpy(d, sp, n);
+    }
+    CK(cudaMemcpyAsync((char*)dst + done, d, n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->stg_ev[sidx], c->stream));
+    done += n;
+  }
+  return B200M_OK;
+}
+
 static int alloc_view_buffers(b200m_ctx* c, ViewHost& v, const void* desc) {
   const size_t esz = v.dtype == DT_F32 ? 4 : 1;
   const size_t bytes = (size_t)v.m * v.dim * esz;
   CK(cudaMallocAsync(&v.raw, std::max<size_t>(bytes, 256), c->stream));
-  CK(cudaMemcpyAsync(v.raw, desc, bytes, cudaMemcpyHostToDevice, c->stream));
+  int rc = staged_h2d(c, v.raw, desc, bytes);
+  if (rc) return rc;
   if (v.tc_capable()) {
     v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
     CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
@@ -201,8 +252,11 @@ static int ensure_view_capacity(b200m_ctx* c, int need) {
   if (need <= c->view_cap) return B200M_OK;
   int cap = std::max(256, c->view_cap * 2);
   while (cap < need) cap *= 2;
-  ViewDev* nv = nullptr; uint32_t* nf = nullptr;
+  ViewDev* nv = nullptr; uint32_t* nf = nullptr; ViewDev* nh = nullptr;
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMallocHost((void**)&nh, sizeof(ViewDev) * cap));
+  if (c->h_views) { std::memcpy(nh, c->h_views, sizeof(ViewDev) * c->view_cap); cudaFreeHost(c->h_views); }
+  c->h_views = nh;
   CK(cudaMalloc((void**)&nv, sizeof(ViewDev) * cap));
   CK(cudaMalloc((void**)&nf, sizeof(uint32_t) * cap));
   CK(cudaMemset(nf, 0, sizeof(uint32_t) * cap));
@@ -262,10 +316,9 @@ struct DecoBefore {
   }
 };
 
-// recs -> final IndMatches of one directed pair.
-void finish_directed(const Rec* recs, int n, bool hamming, const ViewHost& vi, const ViewHost& vj, std::vector<b200m_match>& out) {
-  out.clear();
-  out.reserve(n);
+// recs -> final IndMatches of one directed pair, written to out[0..n) (capacity n). Returns the number kept.
+int finish_directed(const Rec* recs, int n, bool hamming, bool full, const ViewHost& vi, const ViewHost& vj, b200m_match* out) {
+  int cnt = 0;
   for (int k = 0; k < n; ++k) {
     const Rec& r = recs[k];
     if (r.i == 0xFFFFFFFFu) continue;
@@ -279,28 +332,29 @@ void finish_directed(const Rec* recs, int n, bool hamming, const ViewHost& vi, c
       m.distance_ratio = r.d1 / r.d2;                        // float division, filters.hpp:64
       m.distance = r.d1;
     }
-    out.push_back(m);
+    out[cnt++] = m;
   }
+  if (!full || cnt == 0) return cnt;
   // IndMatch::getDeduplicated (IndMatch.hpp:52-58): every query j appears once, so this is a sort by (i, j).
-  std::sort(out.begin(), out.end(), [](const b200m_match& a, const b200m_match& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
-  if (out.empty()) return;
+  std::sort(out, out + cnt, [](const b200m_match& a, const b200m_match& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
   // IndMatchDecorator::getDeduplicated (IndMatchDecorator.hpp:57-69,84-98)
   const float* xi = vi.xy.data(); const float* xj = vj.xy.data();
   if (vi.generic_pos) {
     // All left x distinct and all left y distinct: two matches are "equivalent" iff they share the left feature,
     // the first inserted (smallest j) wins, and the in-order walk is ascending left y.
-    size_t w = 0;
-    for (size_t k = 0; k < out.size(); ++k)
+    int w = 0;
+    for (int k = 0; k < cnt; ++k)
       if (k == 0 || out[k].i != out[k - 1].i) out[w++] = out[k];
-    out.resize(w);
-    std::sort(out.begin(), out.end(), [xi](const b200m_match& a, const b200m_match& b) { return xi[2 * a.i + 1] < xi[2 * b.i + 1]; });
+    cnt = w;
+    std::sort(out, out + cnt, [xi](const b200m_match& a, const b200m_match& b) { return xi[2 * a.i + 1] < xi[2 * b.i + 1]; });
   } else {
-    std::vector<DecoKey> keys; keys.reserve(out.size());
-    for (const auto& m : out) keys.push_back(DecoKey{xi[2 * m.i], xi[2 * m.i + 1], xj[2 * m.j], xj[2 * m.j + 1], m});
-    std::set<DecoKey, DecoBefore> s(keys.begin(), keys.end());
-    out.clear();
-    for (const auto& k : s) out.push_back(k.m);
+    std::vector<DecoKey> keys; keys.reserve(cnt);
+    for (int k = 0; k < cnt; ++k) { const b200m_match& m = out[k]; keys.push_back(DecoKey{xi[2 * m.i], xi[2 * m.i + 1], xj[2 * m.j], xj[2 * m.j + 1], m}); }
+    std::set<DecoKey, DecoBefore> st(keys.begin(), keys.end());
+    cnt = 0;
+    for (const auto& k : st) out[cnt++] = k.m;
   }
+  return cnt;
 }
 
 }  // namespace
@@ -353,6 +407,7 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
 void b200m_ctx_destroy(b200m_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  c->pool->wait();
   cudaStreamSynchronize(c->stream);
   for (auto& v : c->views) free_view_buffers(c, v);
   cudaStreamSynchronize(c->stream);
@@ -364,6 +419,9 @@ void b200m_ctx_destroy(b200m_ctx* c) {
     if (b.ev_copy) cudaEventDestroy(b.ev_copy);
   }
   for (auto& e : c->tev) cudaEventDestroy(e);
+  for (int k = 0; k < b200m_ctx::NSTG; ++k) { if (c->stg[k]) cudaFreeHost(c->stg[k]); if (c->stg_ev[k]) cudaEventDestroy(c->stg_ev[k]); }
+  if (c->h_views) cudaFreeHost(c->h_views);
+  if (c->d_trace) cudaFree(c->d_trace);
   cudaFree(c->d_views); cudaFree(c->d_flags); cudaFree(c->d_err);
   cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
   cudaStreamDestroy(c->copy_stream);
@@ -415,12 +473,17 @@ int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, i
     c->slot_of[view_id] = slot;
   } else {
     slot = it->second;
+    c->pool->wait();
     free_view_buffers(c, c->views[slot]);
   }
   ViewHost& v = c->views[slot];
   v = ViewHost();
   v.id = view_id; v.m = n; v.dim = dim; v.dtype = dtype;
-  if (xy && n > 0) { v.xy.assign(xy, xy + 2 * (size_t)n); v.generic_pos = positions_generic(v.xy, n); }
+  if (xy && n > 0) {
+    v.xy.assign(xy, xy + 2 * (size_t)n);
+    ViewHost* vp = &v;                                   // deque element: stable address
+    c->pool->submit([vp, n] { vp->generic_pos = positions_generic(vp->xy, n); });   // consumed by the finishing stage only
+  }
   if (n > 0) {
     int rc = alloc_view_buffers(c, v, desc);
     if (rc) return rc;
@@ -431,18 +494,18 @@ int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, i
       v.flags_known = false;
     }
   }
-  ViewDev d;
-  int rc = make_view_dev(c, v, d);
+  int rc = make_view_dev(c, v, c->h_views[slot]);
   if (rc) return rc;
-  // the source descriptor memory is caller-owned and pageable: make the H2D copies complete before returning
-  CK(cudaMemcpyAsync(c->d_views + slot, &d, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  // Descriptors went through the pinned staging ring (the caller's memory is already released); the table entry is
+  // copied out of the pinned mirror, so nothing here needs a stream synchronisation.
+  CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
   return B200M_OK;
 }
 
 int b200m_clear_views(b200m_ctx* c) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
   CK(cudaSetDevice(c->device));
+  c->pool->wait();
   for (auto& v : c->views) free_view_buffers(c, v);
   c->views.clear(); c->slot_of.clear();
   CK(cudaStreamSynchronize(c->stream));
@@ -524,7 +587,12 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
   }
 
   const float ratio_sq = dist_ratio * dist_ratio;   // Square(f_dist_ratio) in float, RegionsMatcher.hpp:150 / numeric.hpp:130
-  std::vector<std::vector<b200m_match>> per_dir(stage == B200M_STAGE_DEVICE ? 0 : dir.size());
+  // finishing output: one slot per directed pair in a flat arena (capacity = its record count), filled by pool tasks
+  std::vector<std::unique_ptr<b200m_match[]>> arena(batches.size());   // uninitialised, one block per batch
+  std::vector<b200m_match*> dir_ptr(dir.size(), nullptr);
+  std::vector<int> dir_len(dir.size(), 0);
+  std::vector<std::unique_ptr<TaskGroup>> groups;
+  for (size_t b = 0; b < batches.size(); ++b) groups.emplace_back(new TaskGroup());
   size_t tev_used = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
   int launches = 0;
@@ -613,6 +681,7 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
       }
       CK(cudaEventSynchronize(bb.ev_meta));
       const int total = bb.h_meta[PAIR_CAP + np];
+      if (bi >= 2) groups[bi - 2]->wait();       // the tasks of batch bi-2 read this pinned record buffer
       if (total > 0) {
         CK(cudaStreamWaitEvent(c->copy_stream, bb.ev_meta, 0));
         CK(cudaMemcpyAsync(bb.h_out, bb.d_out, sizeof(Rec) * (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -620,34 +689,29 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
         CK(cudaEventSynchronize(bb.ev_copy));
       }
       total_records += total;
-      // finishing tasks (one per directed pair) — they read bb.h_out, so they must finish before batch bi+2 copies into it
+      // finishing tasks (one per directed pair) run behind the GPU: they only have to be done before batch bi+2's records
+      // are copied into the same pinned buffer.  The per-pair counts/offsets are copied out of the pinned meta block first,
+      // because enqueue(bi+2) overwrites it.
+      arena[bi].reset(new b200m_match[std::max(total, 1)]);
+      TaskGroup* grp = groups[bi].get();
+      int ntasks = 0;
+      for (int p = 0; p < np; ++p) if (dir[B.begin + p].mode != PM_SKIP && bb.h_meta[p] > 0) ++ntasks;
+      grp->add(ntasks);
       for (int p = 0; p < np; ++p) {
         const size_t di = B.begin + p;
         const Directed d = dir[di];
-        if (d.mode == PM_SKIP) continue;
+        dir_ptr[di] = arena[bi].get() + bb.h_meta[PAIR_CAP + p];
         const int cnt = bb.h_meta[p];
+        if (d.mode == PM_SKIP || cnt == 0) continue;
         const Rec* recs = bb.h_out + bb.h_meta[PAIR_CAP + p];
-        std::vector<b200m_match>* dst = &per_dir[di];
+        b200m_match* dst = dir_ptr[di];
+        int* len = &dir_len[di];
         const ViewHost* vi = &c->views[d.slot_i]; const ViewHost* vj = &c->views[d.slot_j];
-        const bool ham = d.mode == PM_HAMMING;
-        if (stage == B200M_STAGE_FULL) {
-          c->pool->submit([=] { finish_directed(recs, cnt, ham, *vi, *vj, *dst); });
-        } else {
-          c->pool->submit([=] {
-            dst->clear();
-            for (int k = 0; k < cnt; ++k) {
-              const Rec& r = recs[k];
-              if (r.i == 0xFFFFFFFFu) continue;
-              b200m_match m; m.i = r.i; m.j = r.j;
-              if (ham) { uint32_t d1, d2; std::memcpy(&d1, &r.d1, 4); std::memcpy(&d2, &r.d2, 4); m.distance_ratio = (float)(d1 / d2); m.distance = (float)d1; }
-              else { m.distance_ratio = r.d1 / r.d2; m.distance = r.d1; }
-              dst->push_back(m);
-            }
-          });
-        }
+        const bool ham = d.mode == PM_HAMMING, full = stage == B200M_STAGE_FULL;
+        c->pool->submit([=] { *len = finish_directed(recs, cnt, ham, full, *vi, *vj, dst); grp->done(); });
       }
-      c->pool->wait();
     }
+    for (auto& g : groups) g->wait();
     if (batches.empty()) CK(cudaEventRecord(c->ev_end, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -661,29 +725,50 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
   CK(cudaMemcpy(&errs, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost));
   c->err_total = errs;
 
-  // ---- assemble
+  // ---- assemble: offsets first, then the per-pair copies into one contiguous block in parallel on the pool
   std::unique_ptr<b200m_result> res(new b200m_result());
   res->pair_ids.reserve(2 * fwd.size());
-  res->offsets.reserve(fwd.size() + 1);
-  res->offsets.push_back(0);
+  res->offsets.assign(fwd.size() + 1, 0);
   const size_t step = do_cross ? 2 : 1;
+  if (stage != B200M_STAGE_DEVICE && do_cross) {
+    // keep m iff (m.j, m.i) is in the reverse list (ImageCollectionMatcher_generic.cpp:92-109); filtered in place, in parallel
+    TaskGroup g; g.add((int)fwd.size());
+    for (size_t k = 0; k < fwd.size(); ++k) {
+      b200m_match* f = dir_ptr[k * step]; int* nf = &dir_len[k * step];
+      const b200m_match* r = dir_ptr[k * step + 1]; const int nr = dir_len[k * step + 1];
+      TaskGroup* gp = &g;
+      c->pool->submit([=] {
+        std::vector<std::pair<uint32_t, uint32_t>> rv; rv.reserve(nr);
+        for (int e = 0; e < nr; ++e) rv.push_back({r[e].i, r[e].j});
+        std::sort(rv.begin(), rv.end());
+        int w = 0;
+        for (int e = 0; e < *nf; ++e)
+          if (std::binary_search(rv.begin(), rv.end(), std::make_pair(f[e].j, f[e].i))) f[w++] = f[e];
+        *nf = w;
+        gp->done();
+      });
+    }
+    g.wait();
+  }
   for (size_t k = 0; k < fwd.size(); ++k) {
     res->pair_ids.push_back(fwd[k].first); res->pair_ids.push_back(fwd[k].second);
-    if (stage != B200M_STAGE_DEVICE) {
-      std::vector<b200m_match>& f = per_dir[k * step];
-      if (do_cross) {
-        // keep m iff (m.j, m.i) is in the reverse list (ImageCollectionMatcher_generic.cpp:92-109)
-        std::vector<std::pair<uint32_t, uint32_t>> rv;
-        rv.reserve(per_dir[k * step + 1].size());
-        for (auto& m : per_dir[k * step + 1]) rv.push_back({m.i, m.j});
-        std::sort(rv.begin(), rv.end());
-        for (auto& m : f)
-          if (std::binary_search(rv.begin(), rv.end(), std::make_pair(m.j, m.i))) res->matches.push_back(m);
-      } else {
-        res->matches.insert(res->matches.end(), f.begin(), f.end());
-      }
+    res->offsets[k + 1] = res->offsets[k] + (stage != B200M_STAGE_DEVICE ? dir_len[k * step] : 0);
+  }
+  const size_t total_matches = (size_t)res->offsets[fwd.size()];
+  res->matches.reset(new b200m_match[std::max<size_t>(total_matches, 1)]);
+  if (total_matches) {
+    const size_t CHUNK_PAIRS = 64;
+    TaskGroup g; g.add((int)((fwd.size() + CHUNK_PAIRS - 1) / CHUNK_PAIRS));
+    for (size_t k0 = 0; k0 < fwd.size(); k0 += CHUNK_PAIRS) {
+      const size_t k1 = std::min(fwd.size(), k0 + CHUNK_PAIRS);
+      b200m_match* base = res->matches.get(); const int64_t* offs = res->offsets.data();
+      b200m_match* const* dp = dir_ptr.data(); const int* dl = dir_len.data(); TaskGroup* gp = &g;
+      c->pool->submit([=] {
+        for (size_t k = k0; k < k1; ++k) if (dl[k * step] > 0) std::memcpy(base + offs[k], dp[k * step], sizeof(b200m_match) * (size_t)dl[k * step]);
+        gp->done();
+      });
     }
-    res->offsets.push_back((int64_t)res->matches.size());
+    g.wait();
   }
   *out = res.release();
   return B200M_OK;
@@ -694,7 +779,7 @@ int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int
   if (!r) return fail(B200M_ERR_ARG, "result is null");
   if (pair_ids) *pair_ids = r->pair_ids.data();
   if (offsets) *offsets = r->offsets.data();
-  if (matches) *matches = r->matches.data();
+  if (matches) *matches = r->matches.get();
   return B200M_OK;
 }
 void b200m_result_free(b200m_result* r) { delete r; }

@@ -138,6 +138,30 @@ def default_context(device: int = 0) -> Context:
     return _default_ctx[device]
 
 
+class _ResultOwner:
+    """Owns one b200m_result; freed when the last numpy view onto it is garbage collected."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.b200m_result_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _alias(addr, nbytes: int, dtype, owner) -> np.ndarray:
+    """Zero-copy numpy view of engine-owned memory (keeps `owner` alive through the buffer object)."""
+    if not addr or nbytes <= 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_uint8 * nbytes).from_address(addr)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype)
+
+
 class ArrayMatcherB200:
     """Mirror of matching::ArrayMatcher (Build / SearchNeighbour / SearchNeighbours), bool returns, no exceptions
     on the matcher surface (ArrayMatcher_bruteForce.hpp:42-51,63-85,98-142)."""
@@ -232,20 +256,13 @@ class ImageCollectionMatcherB200:
         res = C.c_void_p()
         _check(lib.b200m_match_pairs(self.ctx._h, p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_float(self.distRatio),
                                      C.c_int(int(self.crossMatching)), C.c_int(stage), C.byref(res)), "b200m_match_pairs")
-        try:
-            n = lib.b200m_result_num_pairs(res)
-            pid, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            _check(lib.b200m_result_get(res, C.byref(pid), C.byref(off), C.byref(mat)), "b200m_result_get")
-            offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), (n + 1,)).copy() if n >= 0 else np.zeros(1, np.int64)
-            pair_ids = np.ctypeslib.as_array(C.cast(pid, C.POINTER(C.c_uint32)), (n, 2)).copy() if n else np.zeros((0, 2), np.uint32)
-            total = int(offsets[-1])
-            if total:
-                raw = np.ctypeslib.as_array(C.cast(mat, C.POINTER(C.c_uint8)), (total * MATCH_DTYPE.itemsize,)).copy()
-                matches = raw.view(MATCH_DTYPE)
-            else:
-                matches = np.zeros(0, MATCH_DTYPE)
-        finally:
-            lib.b200m_result_free(res)
+        owner = _ResultOwner(lib, res)      # the numpy arrays below alias the result's memory; it is freed when they die
+        n = lib.b200m_result_num_pairs(res)
+        pid, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib.b200m_result_get(res, C.byref(pid), C.byref(off), C.byref(mat)), "b200m_result_get")
+        offsets = _alias(off.value, (n + 1) * 8, np.int64, owner)
+        pair_ids = _alias(pid.value, n * 8, np.uint32, owner).reshape(-1, 2)
+        matches = _alias(mat.value, int(offsets[-1]) * MATCH_DTYPE.itemsize, MATCH_DTYPE, owner)
         return pair_ids, offsets, matches
 
     def Match(self, regionsPerView: dict, pairs, map_PutativesMatches: dict | None = None) -> dict:
@@ -257,7 +274,7 @@ class ImageCollectionMatcherB200:
         for k in range(pair_ids.shape[0]):
             a, b = int(offsets[k]), int(offsets[k + 1])
             if b > a:
-                out[(int(pair_ids[k, 0]), int(pair_ids[k, 1]))] = matches[a:b].copy()
+                out[(int(pair_ids[k, 0]), int(pair_ids[k, 1]))] = matches[a:b]     # view into the engine's result arena
         return out
 
 

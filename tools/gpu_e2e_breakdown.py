@@ -1,0 +1,20 @@
+"""Where does the end-to-end time go? (debug)"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from alicevision_b200 import EMatcherType, ImageCollectionMatcherB200, matching, synth
+n_img = 100
+descs, xys = synth.sift_images(n_img, 8192, np.float32, seed=synth.SEED_DATA, pool_factor=1.0)
+pairs = synth.exhaustive_pairs(n_img)
+views = {i: (descs[i], xys[i]) for i in range(n_img)}
+m = ImageCollectionMatcherB200(0.8, False, EMatcherType.BRUTE_FORCE_L2_B200)
+for rep in range(3):
+    m.clear()
+    t0 = time.perf_counter(); m.upload(views); t1 = time.perf_counter()
+    m.match_uploaded(pairs, matching.STAGE_DEVICE); t2 = time.perf_counter()
+    m.match_uploaded(pairs, matching.STAGE_RAW); t3 = time.perf_counter()
+    pid, off, mat = m.match_uploaded(pairs, matching.STAGE_FULL); t4 = time.perf_counter()
+    print(f"rep {rep}: upload {1e3*(t1-t0):.1f} ms | device {1e3*(t2-t1):.1f} | raw {1e3*(t3-t2):.1f} | full {1e3*(t4-t3):.1f} | gpu_ms {m.ctx.last_gpu_ms():.1f} | matches {len(mat)} records {m.ctx.last_records()}")
+u8 = {i: (descs[i].astype(np.uint8), xys[i]) for i in range(n_img)}
+m.clear(); t0 = time.perf_counter(); m.upload(u8); print("upload u8:", 1e3 * (time.perf_counter() - t0), "ms")
