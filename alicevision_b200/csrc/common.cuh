@@ -40,7 +40,8 @@ struct PairDev {
   uint32_t cand_base;        // first candidate slot of this pair (prefix sum of m_j over the batch)
   uint32_t mode;             // PM_*
 };
-enum : uint32_t { PM_TC = 0, PM_EXACT_F32 = 1, PM_EXACT_U8 = 2, PM_HAMMING = 3, PM_SKIP = 4 };
+enum : uint32_t { PM_TC = 0, PM_EXACT_F32 = 1, PM_EXACT_U8 = 2, PM_HAMMING = 3, PM_SKIP = 4,
+                  PM_TC_FUSED = 5 /* tensor-core pair whose kernel also ran the exactness pass: candidates are final */ };
 
 // Work item of the tensor-core kernel: 128 consecutive queries of pair `pair` against the whole database image.
 struct WorkItem { uint32_t pair, qtile; };

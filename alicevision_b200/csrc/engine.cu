@@ -608,7 +608,9 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     for (int p = 0; p < np; ++p) {
       const Directed& d = dir[B.begin + p];
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
-      bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, d.mode};
+      // the CTA-pair kernel runs the exactness pass itself: its candidates are final records
+      const uint32_t dev_mode = (d.mode == PM_TC && c->tc_variant >= 2) ? (uint32_t)PM_TC_FUSED : d.mode;
+      bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, dev_mode};
       cbase += (uint32_t)vj.m;
       const int qrows = c->tc_variant >= 2 ? 2 * tc2::BM : tc::BM;   // queries per work item
       if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + qrows - 1) / qrows; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
@@ -624,9 +626,9 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     if (n_items && c->tc_variant >= 2) {
       const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
       if (c->tc_variant == 3)
-        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate);
+        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err);
       else
-        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate);
+        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err);
       ++launches;
     } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);

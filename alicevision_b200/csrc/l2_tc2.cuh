@@ -8,12 +8,17 @@
 //
 // Work item = 256 consecutive queries of J (128 per CTA of the pair) x the whole database image I.
 //   every CTA : warp 0 TMA producer (own Q tile, own half of each DB tile, full 256-entry half-norm chunk),
-//               warp 2 TMEM allocator (cta_group::2), warps 4-11 epilogue on its own 128 accumulator rows
+//               warp 2 TMEM allocator (cta_group::2), then, with warp 3, the EXACTNESS PASS of the previous work item:
+//               the epilogue queues its candidates in shared memory and these two otherwise idle warps re-score them
+//               (verify.cuh rescore_candidate) and append the final records while the next item streams through the
+//               tensor pipe, so the match list is complete when the kernel ends: no second pass over the pairs;
+//               warps 4.. epilogue on its own 128 accumulator rows
 //   leader CTA: warp 1 issues tcgen05.mma.cta_group::2; completions are multicast to both CTAs' barriers
 // Barrier homes: q_full / db_full / tm_empty live in the LEADER (TMA bytes of both CTAs and the epilogue arrivals of
 // both CTAs are credited there); q_empty / db_empty / tm_full / nb_full / nb_empty are per CTA.
 #pragma once
 #include "l2_tc.cuh"
+#include "verify.cuh"
 
 namespace b200m {
 namespace tc2 {
@@ -30,15 +35,17 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
 constexpr int OFF_NB = OFF_DB + NS * DBH_BYTES;
 constexpr int OFF_MRG = OFF_NB + NS * NB_BYTES;
-constexpr int OFF_BAR = OFF_MRG + 2 * 3 * BM * 16;   // double-buffered, up to 3 partial top-2 records per row
-constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS;
+constexpr int OFF_VQ = OFF_MRG + 2 * 3 * BM * 16;    // candidate queue: 2 buffers x 128 Cand (one slot range of 32 per epilogue quadrant)
+constexpr int OFF_VQN = OFF_VQ + 2 * BM * 16;        // 2 x (4 per-quadrant counts + pair index), 32 B each
+constexpr int OFF_BAR = OFF_VQN + 2 * 32;
+constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS + 2 + 2;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
 template <int EPI_WARPS>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
 l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
-                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg) {
+                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count) {
   long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
@@ -51,6 +58,8 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
   uint64_t* tm_empty = tm_full + 2;         // [2]  leader, 16 arrivals (8 epilogue warps x 2 CTAs)
   uint64_t* nb_full = tm_empty + 2;         // [NS] per CTA (half-norm ring, same index as the database stage)
   uint64_t* nb_empty = nb_full + NS;        // [NS] per CTA, 8 arrivals
+  uint64_t* vq_full = nb_empty + NS;        // [2]  per CTA, 4 arrivals (the epilogue quadrants that emit candidates)
+  uint64_t* vq_empty = vq_full + 2;         // [2]  per CTA, 2 arrivals (the two exactness-pass warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
@@ -64,6 +73,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
       ptx::mbar_init(&tm_full[i], 1); ptx::mbar_init(&tm_empty[i], 2 * EPI_WARPS);
     }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&vq_full[i], 4); ptx::mbar_init(&vq_empty[i], 2); }
     for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&db_full[i], 1); ptx::mbar_init(&db_empty[i], 1);
       ptx::mbar_init(&nb_full[i], 1); ptx::mbar_init(&nb_empty[i], EPI_WARPS);
@@ -159,6 +169,32 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         qb ^= 1; if (qb == 0) qph ^= 1;
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ exactness pass of the previous item (2 warps)
+    uint32_t par = 0, vph = 0;
+    for (int it = cluster_id; it < n_items; it += n_clusters) {
+      ptx::mbar_wait(&vq_full[par], vph);
+      const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + OFF_VQN + par * 32);
+      const PairDev p = pairs[hdr[4]];
+      const __half* db16 = views[p.view_i].h16;
+      const __half* q16 = views[p.view_j].h16;
+      const Cand* queue = reinterpret_cast<const Cand*>(smem + OFF_VQ) + par * BM;
+      for (int quad = (warp - 2) * 2; quad < (warp - 2) * 2 + 2; ++quad) {
+        const int n = (int)hdr[quad];
+        for (int e = 0; e < n; ++e) {
+          const Cand k = queue[quad * 32 + e];
+          Rec rec;
+          const bool keep = rescore_candidate(db16, q16, p.m_i, k, ratio_sq, lane, err_count, rec);
+          if (keep && lane == 0) {
+            const int slot = atomicAdd(&cand_count[hdr[4]], 1);
+            cands[p.cand_base + slot] = Cand{rec.j, rec.i, rec.d1, rec.d2};     // final record, (query, database row) order like the exact kernels
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&vq_empty[par]);
+      par ^= 1; if (par == 0) vph ^= 1;
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (EPI_WARPS warps per CTA, own 128 rows)
     constexpr int NQ = EPI_WARPS / 4;            // column groups per stage (2 or 4)
@@ -166,7 +202,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
     const int colq = (warp - 4) >> 2;            // which column group
     const int row = quad * 32 + lane;
-    uint32_t ac = 0, aph = 0, st = 0, sph = 0, par = 0, tt = 0;
+    uint32_t ac = 0, aph = 0, st = 0, sph = 0, par = 0, vqph = 0, tt = 0;
     long long* etrace = (lane == 0 && quad == 0 && colq < 2) ? trace : nullptr;
     for (int it = cluster_id; it < n_items; it += n_clusters) {
       const WorkItem w = items[it];
@@ -174,7 +210,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       const int ntiles = ((int)p.m_i + BN - 1) / BN;
       tc::Top2 s{INFINITY, INFINITY, 0u};
       for (int t = 0; t < ntiles; ++t) {
-        ptx::mbar_wait(&nb_full[st], sph);
+        if (t == 0) ptx::mbar_wait(&nb_full[st], sph);     // later tiles: already observed at the end of the previous tile
         ptx::trace_stamp(etrace, 2 + colq, tt, 0);
         ptx::mbar_wait(&tm_full[ac], aph);
         ptx::trace_stamp(etrace, 2 + colq, tt, 1);
@@ -214,6 +250,9 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         }
         ac ^= 1; if (ac == 0) aph ^= 1;
         if (++st == NS) { st = 0; sph ^= 1; }
+        // the next tile's half-norms landed long ago; observing their barrier now (while the tensor pipe is still busy with
+        // that tile) takes ~100 cycles off the serial MMA -> epilogue -> MMA chain
+        if (t + 1 < ntiles) ptx::mbar_wait(&nb_full[st], sph);
       }
       // merge the column groups of each query row, pre-test, emit candidates
       float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * 3 * BM;
@@ -237,15 +276,17 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           d2 = fmaf(2.f, m2, na);
           keep = d1 < __fmul_rn(ratio_sq, d2);
         }
+        // hand the survivors of the pre-test to the exactness-pass warps through shared memory (32 slots per quadrant)
+        ptx::mbar_wait(&vq_empty[par], vqph ^ 1);          // they finished the item that used this buffer two items ago
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-        if (mask) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&cand_count[w.pair], __popc(mask));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (keep) cands[p.cand_base + base + __popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
-        }
+        Cand* queue = reinterpret_cast<Cand*>(smem + OFF_VQ) + par * BM + quad * 32;
+        if (keep) queue[__popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(smem + OFF_VQN + par * 32);
+        if (lane == 0) { hdr[quad] = (uint32_t)__popc(mask); if (quad == 0) hdr[4] = w.pair; }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&vq_full[par]);
       }
-      par ^= 1;
+      par ^= 1; if (par == 0) vqph ^= 1;
     }
   }
 

@@ -46,6 +46,49 @@ __global__ void scan_counts_kernel(const int* __restrict__ cand_count, int n, in
   if (threadIdx.x == 0) offsets[n] = carry;
 }
 
+// Warp-level exact re-scoring of one tensor-core candidate (see the header comment). All 32 lanes call it with the same
+// candidate; lane l handles database row 16*k.b + (l & 15), components 64*(l >> 4)..+63. Returns (on every lane)
+// whether the match survives the ratio test; `rec` is the final record (i = database row, j = query row, d1, d2).
+__device__ __forceinline__ bool rescore_candidate(const __half* __restrict__ db16, const __half* __restrict__ q16, uint32_t m_i, const Cand& k,
+                                                  float ratio_sq, int lane, unsigned int* __restrict__ err_count, Rec& rec) {
+  const int r = lane & 15, hv = lane >> 4;
+  const uint32_t row = k.b * 16 + r;
+  float acc = INFINITY;
+  if (row < m_i) {
+    const uint4* a = reinterpret_cast<const uint4*>(q16 + (size_t)k.q * 128 + hv * 64);
+    const uint4* b = reinterpret_cast<const uint4*>(db16 + (size_t)row * 128 + hv * 64);
+    acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const uint4 x = a[v], y = b[v];
+      const __half2* xh = reinterpret_cast<const __half2*>(&x);
+      const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fx = __half22float2(xh[e]), fy = __half22float2(yh[e]);
+        const float d0 = fx.x - fy.x, d1 = fx.y - fy.y;
+        acc = fmaf(d0, d0, acc);
+        acc = fmaf(d1, d1, acc);
+      }
+    }
+  }
+  const float dist = acc + __shfl_xor_sync(0xffffffffu, acc, 16);      // INF for rows past the end
+  float best = dist; int arg = r;                                        // argmin over the 16 rows (ties -> smallest row)
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  float second = (r == arg) ? INFINITY : dist;
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) second = fminf(second, __shfl_xor_sync(0xffffffffu, second, o));
+  if (lane == 0 && best != k.d1) atomicAdd(err_count, 1u);             // tensor-core accumulation was not exact
+  const float d2 = fminf(k.d2, second);
+  rec = Rec{k.b * 16 + (uint32_t)arg, k.q, best, d2};
+  return best < __fmul_rn(ratio_sq, d2);                                // matching/filters.hpp:60
+}
+
 constexpr int VERIFY_BLOCKS_PER_PAIR = 4;
 constexpr int VERIFY_WARPS = 8;
 
@@ -60,7 +103,7 @@ verify_pack_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
   const int nwarps = gridDim.y * VERIFY_WARPS;
   const Cand* src = cands + p.cand_base;
   Rec* dst = out + offsets[blockIdx.x];
-  if (p.mode != PM_TC) {
+  if (p.mode != PM_TC) {      // exact / Hamming pairs, and tensor-core pairs whose candidates were already re-scored in-kernel
     for (int c = wid * 32 + lane; c < n; c += nwarps * 32) {
       const Cand k = src[c];
       dst[c] = Rec{k.b, k.q, k.d1, k.d2};
@@ -69,48 +112,11 @@ verify_pack_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
   }
   const ViewDev& vi = views[p.view_i];
   const ViewDev& vj = views[p.view_j];
-  const int r = lane & 15, hv = lane >> 4;   // database row inside the chunk, which 64-component half
   for (int c = wid; c < n; c += nwarps) {
     const Cand k = src[c];
-    const uint32_t row = k.b * 16 + r;
-    float acc = INFINITY;
-    if (row < p.m_i) {
-      const uint4* a = reinterpret_cast<const uint4*>(vj.h16 + (size_t)k.q * 128 + hv * 64);
-      const uint4* b = reinterpret_cast<const uint4*>(vi.h16 + (size_t)row * 128 + hv * 64);
-      acc = 0.f;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const uint4 x = a[v], y = b[v];
-        const __half2* xh = reinterpret_cast<const __half2*>(&x);
-        const __half2* yh = reinterpret_cast<const __half2*>(&y);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 fx = __half22float2(xh[e]), fy = __half22float2(yh[e]);
-          const float d0 = fx.x - fy.x, d1 = fx.y - fy.y;
-          acc = fmaf(d0, d0, acc);
-          acc = fmaf(d1, d1, acc);
-        }
-      }
-    }
-    const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
-    const float dist = acc + other;      // INF for rows past the end
-    // argmin over the 16 rows (ties -> smallest row), then second minimum
-    float best = dist; int arg = r;
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-    }
-    float second = (r == arg) ? INFINITY : dist;
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) second = fminf(second, __shfl_xor_sync(0xffffffffu, second, o));
-    if (lane == 0) {
-      if (best != k.d1) atomicAdd(err_count, 1u);
-      const float d2 = fminf(k.d2, second);
-      const bool keep = best < __fmul_rn(ratio_sq, d2);
-      dst[c] = keep ? Rec{k.b * 16 + (uint32_t)arg, k.q, best, d2} : Rec{0xFFFFFFFFu, k.q, best, d2};
-    }
+    Rec rec;
+    const bool keep = rescore_candidate(vi.h16, vj.h16, p.m_i, k, ratio_sq, lane, err_count, rec);
+    if (lane == 0) dst[c] = keep ? rec : Rec{0xFFFFFFFFu, k.q, rec.d1, rec.d2};
   }
 }
 
