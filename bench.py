@@ -119,6 +119,7 @@ def cpu_baseline(descs, xys, pairs, hamming, budget_s):
     """The reference's CPU brute force (+ ratio test + de-duplication) on a bounded sample of the same pair list."""
     import oracle
     ora = oracle.best()
+    ora.set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the baseline gets every CPU this process may use
     n = 0
     t0 = time.perf_counter()
     while n < len(pairs) and (time.perf_counter() - t0) < budget_s:
@@ -149,10 +150,10 @@ def main():
         # Reference arm: the reference's own CPU implementation on the box's host cores, rank 0 only.
         if rank != 0:
             return
-        descs, xys, pairs = make_workload(argparse.Namespace(**{**vars(args), "images": args.images or 8}), 1)
+        descs, xys, pairs = make_workload(argparse.Namespace(**{**vars(args), "images": args.images or 24}), 1)
         per_step = []
         for s in range(args.warmup + args.steps):
-            b = cpu_baseline(descs, xys, pairs[s % 4::4], hamming, max(2.0, args.cpu_seconds / 2))
+            b = cpu_baseline(descs, xys, pairs[s % 4::4], hamming, max(2.0, args.cpu_seconds / 2))   # ~6 s of CPU work per step
             if s >= args.warmup:
                 per_step.append(b)
         v = float(np.mean([b["value"] for b in per_step])) if per_step else 0.0
