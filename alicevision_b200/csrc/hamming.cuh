@@ -6,7 +6,9 @@
 //
 // One thread owns one query (16 x u32 in registers); the database image is streamed through shared memory in
 // 256-row tiles (16 KB) and read with warp-broadcast LDS.128, so HBM/L2 traffic is one pass over the database
-// per 256 queries.  16 XOR + 16 POPC + adds per (query,row): the kernel is bound by the integer/popc pipe.
+// per 256 queries.  The first version (16 XOR + 16 POPC per (query,row)) ran the POPC (XU) pipe at 97.7 % (ncu,
+// profiles/r01_ncu_hamming_top2_kernel.md) with the ALU pipe at 42 %; the 16 XOR words are now folded with a
+// carry-save adder tree (11 full adders = 22 LOP3) down to five words of weight 1,1,2,4,8, so only 5 POPC remain.
 #pragma once
 #include "common.cuh"
 
@@ -14,6 +16,30 @@ namespace b200m {
 
 constexpr int HM_TQ = 256;     // queries per block (one per thread)
 constexpr int HM_TD = 256;     // database rows per smem tile
+
+// full adder on 32 bit-columns at once: l = a^b^c (weight 1), h = majority(a,b,c) (weight 2)
+__device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(a), "r"(b), "r"(c));
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(a), "r"(b), "r"(c));
+}
+// popcount of 16 words = sum of popc over 512 bits, exact (feature/Hamming.hpp:120-129 sums eight popcountll)
+__device__ __forceinline__ uint32_t popc512(const uint4& a0, const uint4& a1, const uint4& a2, const uint4& a3,
+                                            const uint4& b0, const uint4& b1, const uint4& b2, const uint4& b3) {
+  const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+  const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+  const uint32_t x8 = a2.x ^ b2.x, x9 = a2.y ^ b2.y, x10 = a2.z ^ b2.z, x11 = a2.w ^ b2.w;
+  const uint32_t x12 = a3.x ^ b3.x, x13 = a3.y ^ b3.y, x14 = a3.z ^ b3.z, x15 = a3.w ^ b3.w;
+  uint32_t c0, c1, c2, c3, c4, s0, s1, s2, s3, s4;           // level 1: 15 words -> 5 ones + 5 twos
+  csa(c0, s0, x0, x1, x2); csa(c1, s1, x3, x4, x5); csa(c2, s2, x6, x7, x8); csa(c3, s3, x9, x10, x11); csa(c4, s4, x12, x13, x14);
+  uint32_t d0, d1, t0, t1;                                   // ones: s0..s4, x15 -> t0, t1 (+ twos d0, d1)
+  csa(d0, t0, s0, s1, s2); csa(d1, t1, s3, s4, x15);
+  uint32_t e0, e1, u0, u1;                                   // twos: c0..c4, d0, d1 -> u0, u1, d1 (+ fours e0, e1)
+  csa(e0, u0, c0, c1, c2); csa(e1, u1, c3, c4, d0);
+  uint32_t f, v, g, w;
+  csa(f, v, u0, u1, d1);                                     // twos -> v (+ four f)
+  csa(g, w, f, e0, e1);                                      // fours -> w (+ eight g)
+  return __popc(t0) + __popc(t1) + 2u * __popc(v) + 4u * __popc(w) + 8u * __popc(g);
+}
 
 template <bool OUT_DENSE>
 __global__ void __launch_bounds__(HM_TQ)
@@ -37,10 +63,7 @@ hamming_top2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
       const uint4 b0 = tile[r * 4], b1 = tile[r * 4 + 1], b2 = tile[r * 4 + 2], b3 = tile[r * 4 + 3];
-      uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w);
-      d += __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-      d += __popc(a2.x ^ b2.x) + __popc(a2.y ^ b2.y) + __popc(a2.z ^ b2.z) + __popc(a2.w ^ b2.w);
-      d += __popc(a3.x ^ b3.x) + __popc(a3.y ^ b3.y) + __popc(a3.z ^ b3.z) + __popc(a3.w ^ b3.w);
+      const uint32_t d = popc512(a0, a1, a2, a3, b0, b1, b2, b3);
       // rows arrive in increasing index order, so strict '<' keeps (value, index) lexicographic order
       if (d < m2) {
         if (d < m1) { m2 = m1; i2 = i1; m1 = d; i1 = d0 + r; }

@@ -115,11 +115,31 @@ class ClockSampler:
                 "samples": len(rows), "reasons": sorted(reasons)}
 
 
+def host_cores() -> int:
+    """Physical cores this process may run on ("all physical cores"); hyper-threads only slow the reference's
+    compute-bound OpenMP loop down.  Falls back to the affinity count."""
+    allowed = os.sched_getaffinity(0)
+    try:
+        cores, cpu, phys = set(), None, None
+        for line in open("/proc/cpuinfo"):
+            k, _, v = line.partition(":")
+            k = k.strip()
+            if k == "processor":
+                cpu, phys = int(v), None
+            elif k == "physical id":
+                phys = int(v)
+            elif k == "core id" and cpu in allowed:
+                cores.add((phys, int(v)))
+        return len(cores) or len(allowed)
+    except Exception:
+        return len(allowed)
+
+
 def cpu_baseline(descs, xys, pairs, hamming, budget_s):
     """The reference's CPU brute force (+ ratio test + de-duplication) on a bounded sample of the same pair list."""
     import oracle
     ora = oracle.best()
-    ora.set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the baseline gets every CPU this process may use
+    ora.set_num_threads(host_cores())   # torchrun exports OMP_NUM_THREADS=1; the baseline gets every physical core this process may use
     n = 0
     t0 = time.perf_counter()
     while n < len(pairs) and (time.perf_counter() - t0) < budget_s:
