@@ -604,12 +604,17 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     BatchBuf& bb = c->buf[bi & 1];
     const int np = (int)(B.end - B.begin);
     uint32_t cbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
+    // In-kernel exactness pass only when a work item lasts long enough (>= 24 database tiles on average) for two warps to
+    // re-score the previous item's candidates behind it; shorter images use the stand-alone exactness kernel.
+    long tc_rows = 0, tc_n = 0;
+    for (int p = 0; p < np; ++p) if (dir[B.begin + p].mode == PM_TC) { tc_rows += c->views[dir[B.begin + p].slot_i].m; ++tc_n; }
+    const bool fused = c->tc_variant >= 2 && tc_n > 0 && tc_rows / tc_n >= 6144;
     bool any_f32 = false, any_u8 = false, any_ham = false;
     for (int p = 0; p < np; ++p) {
       const Directed& d = dir[B.begin + p];
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
       // the CTA-pair kernel runs the exactness pass itself: its candidates are final records
-      const uint32_t dev_mode = (d.mode == PM_TC && c->tc_variant >= 2) ? (uint32_t)PM_TC_FUSED : d.mode;
+      const uint32_t dev_mode = (d.mode == PM_TC && fused) ? (uint32_t)PM_TC_FUSED : d.mode;
       bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, dev_mode};
       cbase += (uint32_t)vj.m;
       const int qrows = c->tc_variant >= 2 ? 2 * tc2::BM : tc::BM;   // queries per work item
@@ -626,9 +631,9 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     if (n_items && c->tc_variant >= 2) {
       const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
       if (c->tc_variant == 3)
-        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err);
+        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
       else
-        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err);
+        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
       ++launches;
     } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);

@@ -45,7 +45,7 @@ constexpr int SMEM_BYTES = OFF_TMEM + 16;
 template <int EPI_WARPS>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
 l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
-                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count) {
+                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count, int fused) {
   long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
@@ -171,8 +171,10 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
     }
   } else if (warp == 2 || warp == 3) {
     // ------------------------------------------------------------------ exactness pass of the previous item (2 warps)
+    // fused == 0 (short database images: an item lasts only a few tiles, two warps cannot hide the re-scoring latency):
+    // the epilogue writes its candidates to global memory and the stand-alone exactness kernel handles them.
     uint32_t par = 0, vph = 0;
-    for (int it = cluster_id; it < n_items; it += n_clusters) {
+    for (int it = cluster_id; fused && it < n_items; it += n_clusters) {
       ptx::mbar_wait(&vq_full[par], vph);
       const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + OFF_VQN + par * 32);
       const PairDev p = pairs[hdr[4]];
@@ -276,15 +278,22 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           d2 = fmaf(2.f, m2, na);
           keep = d1 < __fmul_rn(ratio_sq, d2);
         }
-        // hand the survivors of the pre-test to the exactness-pass warps through shared memory (32 slots per quadrant)
-        ptx::mbar_wait(&vq_empty[par], vqph ^ 1);          // they finished the item that used this buffer two items ago
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-        Cand* queue = reinterpret_cast<Cand*>(smem + OFF_VQ) + par * BM + quad * 32;
-        if (keep) queue[__popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
-        uint32_t* hdr = reinterpret_cast<uint32_t*>(smem + OFF_VQN + par * 32);
-        if (lane == 0) { hdr[quad] = (uint32_t)__popc(mask); if (quad == 0) hdr[4] = w.pair; }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&vq_full[par]);
+        if (fused) {
+          // hand the survivors of the pre-test to the exactness-pass warps through shared memory (32 slots per quadrant)
+          ptx::mbar_wait(&vq_empty[par], vqph ^ 1);        // they finished the item that used this buffer two items ago
+          Cand* queue = reinterpret_cast<Cand*>(smem + OFF_VQ) + par * BM + quad * 32;
+          if (keep) queue[__popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
+          uint32_t* hdr = reinterpret_cast<uint32_t*>(smem + OFF_VQN + par * 32);
+          if (lane == 0) { hdr[quad] = (uint32_t)__popc(mask); if (quad == 0) hdr[4] = w.pair; }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&vq_full[par]);
+        } else if (mask) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&cand_count[w.pair], __popc(mask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) cands[p.cand_base + base + __popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
+        }
       }
       par ^= 1; if (par == 0) vqph ^= 1;
     }
