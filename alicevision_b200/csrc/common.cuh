@@ -22,10 +22,12 @@ enum : uint32_t {
 struct alignas(128) ViewDev {
   CUtensorMap tmap128;  // fp16 [m x 128], box {64 x 128 rows}, SWIZZLE_128B (query tiles; only when dim == 128 scalar)
   CUtensorMap tmap256;  // same tensor, box {64 x 256 rows}: one box = one K-half of a database tile
+  CUtensorMap tmap_aug; // fp16 [m_pad x 16] half-norm limbs, box {16 x 128 rows}, SWIZZLE_32B (9th K-step of the AUG kernel)
   const void* raw;      // original descriptors, row-major m x dim (f32 / u8 / 64-byte binary)
   const __half* h16;    // fp16 copy (scalar, dim == 128) or nullptr
   const float* nbh;     // ||row||^2 / 2, padded to a multiple of 256 rows with 1e30f
   const float* nrm;     // ||row||^2
+  const __half* aug16;  // m_pad x 16: [b0, l0, l1, 0...] with ||row||^2/2 = 0.5*b0 + l0 + 2048*l1; pad rows [0, 0, 2047]
   int32_t m;            // number of regions
   int32_t dim;          // components (scalar) or bytes (binary)
   int32_t dtype;

@@ -99,7 +99,7 @@ struct TaskGroup {
 struct ViewHost {
   uint32_t id = 0;
   int m = 0, dim = 0, dtype = 0, m_pad = 0;
-  void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr;
+  void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr;
   std::vector<float> xy;      // m x 2 positions (host only; used by the finishing stage)
   bool generic_pos = false;   // all x distinct and all y distinct
   uint32_t flags = 0; bool flags_known = true;
@@ -142,7 +142,8 @@ struct b200m_ctx {
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   std::unique_ptr<Pool> pool;
   bool force_exact = false;
-  int tc_variant = 2;             // 1 = single-CTA kernel (l2_tc.cuh), 2 / 3 = CTA-pair kernel (l2_tc2.cuh) with 8 / 16 epilogue warps
+  int tc_variant = 4;             // 1 = single-CTA kernel (l2_tc.cuh); CTA-pair kernel (l2_tc2.cuh): 2 = 8 epilogue warps, 3 = 16 epilogue warps,
+                                  // 4 (default) = 8 epilogue warps + half-norms folded into the GEMM (AUG)
   // last-call instrumentation
   double last_gpu_ms = 0, last_search_ms = 0; int last_launches = 0, last_tc_pairs = 0; int64_t last_records = 0;
   unsigned err_total = 0;
@@ -203,6 +204,7 @@ static int alloc_view_buffers(b200m_ctx* c, ViewHost& v, const void* desc) {
     CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
     CK(cudaMallocAsync((void**)&v.nbh, (size_t)v.m_pad * 4, c->stream));
     CK(cudaMallocAsync((void**)&v.nrm, (size_t)v.m_pad * 4, c->stream));
+    CK(cudaMallocAsync((void**)&v.aug16, (size_t)v.m_pad * 32, c->stream));
   }
   return B200M_OK;
 }
@@ -211,12 +213,13 @@ static void free_view_buffers(b200m_ctx* c, ViewHost& v) {
   if (v.h16) cudaFreeAsync(v.h16, c->stream);
   if (v.nbh) cudaFreeAsync(v.nbh, c->stream);
   if (v.nrm) cudaFreeAsync(v.nrm, c->stream);
-  v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr;
+  if (v.aug16) cudaFreeAsync(v.aug16, c->stream);
+  v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr; v.aug16 = nullptr;
 }
 
 static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   std::memset(&d, 0, sizeof(d));
-  d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.m = v.m; d.dim = v.dim; d.dtype = v.dtype;
+  d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.aug16 = v.aug16; d.m = v.m; d.dim = v.dim; d.dtype = v.dtype;
   if (v.tc_capable()) {
     const cuuint64_t gdim[2] = {128, (cuuint64_t)v.m};
     const cuuint64_t gstr[1] = {256};
@@ -228,6 +231,14 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
     }
+    {
+      const cuuint64_t adim[2] = {16, (cuuint64_t)v.m_pad};
+      const cuuint64_t astr[1] = {32};
+      const cuuint32_t abox[2] = {16, 128};
+      CUresult r = c->encode(&d.tmap_aug, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.aug16, adim, astr, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled(aug) failed: " + std::to_string((int)r));
+    }
   }
   return B200M_OK;
 }
@@ -235,8 +246,8 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
 static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag) {
   if (!v.tc_capable()) return B200M_OK;
   const int grid = (v.m_pad + 7) / 8;
-  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag);
-  else prep_view_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag);
+  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
+  else prep_view_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
   CK(cudaGetLastError());
   return B200M_OK;
 }
@@ -287,8 +298,9 @@ static int ensure_batch_buffers(b200m_ctx* c) {
     CK(cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming));
   }
   CK(cudaFuncSetAttribute(tc::l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<false>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<false>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
@@ -435,7 +447,7 @@ int b200m_ctx_set_host_threads(b200m_ctx* c, int n) {
   return B200M_OK;
 }
 int b200m_ctx_set_tc_variant(b200m_ctx* c, int variant) {
-  if (!c || variant < 1 || variant > 3) return fail(B200M_ERR_ARG, "tc variant must be 1 (single CTA), 2 (CTA pair, 8 epilogue warps) or 3 (CTA pair, 16 epilogue warps)");
+  if (!c || variant < 1 || variant > 4) return fail(B200M_ERR_ARG, "tc variant must be 1 (single CTA), 2 (CTA pair), 3 (CTA pair, 16 epilogue warps) or 4 (CTA pair, half-norms folded into the GEMM)");
   c->tc_variant = variant;
   return B200M_OK;
 }
@@ -631,9 +643,11 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     if (n_items && c->tc_variant >= 2) {
       const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
       if (c->tc_variant == 3)
-        tc2::l2_top2_tc2_kernel<16><<<grid, 128 + 16 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+        tc2::l2_top2_tc2_kernel<16, false><<<grid, 128 + 16 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+      else if (c->tc_variant == 4)
+        tc2::l2_top2_tc2_kernel<8, true><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
       else
-        tc2::l2_top2_tc2_kernel<8><<<grid, 128 + 8 * 32, tc2::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+        tc2::l2_top2_tc2_kernel<8, false><<<grid, 128 + 8 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
       ++launches;
     } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);

@@ -25,28 +25,41 @@ namespace tc2 {
 
 constexpr int BM = 128;                 // queries per CTA (256 per pair)
 constexpr int BN = 256;                 // database rows per tile (128 staged per CTA)
-constexpr int NS = 4;                   // database smem stages per CTA
 constexpr int Q_BYTES = BM * 128 * 2;   // 32 KB
-constexpr int DBH_BYTES = 128 * 128 * 2;  // 32 KB: this CTA's half of a database tile
+constexpr int DBH_BYTES = 128 * 128 * 2;  // 32 KB: this CTA's half of a database tile (two K-blocks of 64)
+constexpr int AUG_BYTES = 128 * 16 * 2;   // 4 KB: 16 augmentation columns of the same 128 rows (AUG only)
 constexpr int NB_BYTES = BN * 4;
 constexpr int MAX_EPI_WARPS = 16;
 
-constexpr int OFF_Q = 0;
-constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
-constexpr int OFF_NB = OFF_DB + NS * DBH_BYTES;
-constexpr int OFF_MRG = OFF_NB + NS * NB_BYTES;
-constexpr int OFF_VQ = OFF_MRG + 2 * 3 * BM * 16;    // candidate queue: 2 buffers x 128 Cand (one slot range of 32 per epilogue quadrant)
-constexpr int OFF_VQN = OFF_VQ + 2 * BM * 16;        // 2 x (4 per-quadrant counts + pair index), 32 B each
-constexpr int OFF_BAR = OFF_VQN + 2 * 32;
-constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS + 2 + 2;
-constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
+// Shared-memory layout. AUG = the database half-norm is folded into the GEMM as a 9th K-step: each database row carries
+// 16 extra fp16 columns [b0, l0, l1, 0...] with ||b||^2/2 = 0.5*b0 + l0 + 2048*l1 (all three exact in fp16), every query
+// row the constants [-0.5, -1, -2048, 0...]; with B negated by the instruction descriptor the accumulator becomes
+// h = ||b||^2/2 - a.b directly.  That removes the half-norm ring, 32 LDS.128 and 64 FADD2 per thread and tile from
+// the epilogue for 12.5 % more tensor work.
+template <bool AUG> struct Lay {
+  static constexpr int NS = AUG ? 3 : 4;                             // database smem stages per CTA
+  static constexpr int STAGE = DBH_BYTES + (AUG ? AUG_BYTES : 0);
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
+  static constexpr int OFF_NB = OFF_DB + NS * STAGE;                 // non-AUG: half-norm ring; AUG: the constant A tile (4 KB)
+  static constexpr int OFF_MRG = OFF_NB + (AUG ? AUG_BYTES : NS * NB_BYTES);
+  static constexpr int OFF_VQ = OFF_MRG + 2 * 3 * BM * 16;           // candidate queue: 2 buffers x 128 Cand (32 slots per epilogue quadrant)
+  static constexpr int OFF_VQN = OFF_VQ + 2 * BM * 16;               // 2 x (4 per-quadrant counts + pair index), 32 B each
+  static constexpr int OFF_BAR = OFF_VQN + 2 * 32;
+  static constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS + 2 + 2;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+};
+constexpr int SMEM_BYTES = Lay<false>::SMEM_BYTES;
 
-template <int EPI_WARPS>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp)
+template <int EPI_WARPS, bool AUG>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp); AUG: see Lay
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
 l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
                    Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count, int fused) {
   long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
+  using L = Lay<AUG>;
+  constexpr int NS = L::NS, OFF_Q = L::OFF_Q, OFF_DB = L::OFF_DB, OFF_NB = L::OFF_NB, OFF_MRG = L::OFF_MRG, OFF_VQ = L::OFF_VQ,
+                OFF_VQN = L::OFF_VQN, OFF_BAR = L::OFF_BAR, OFF_TMEM = L::OFF_TMEM, STAGE = L::STAGE;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -84,6 +97,18 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
     ptx::tmem_alloc_2sm(tmem_slot, 512);
     ptx::tmem_relinquish_2sm();
   }
+  if (AUG && warp >= 4 && warp < 8) {
+    // the constant augmentation tile of the A operand: 128 rows x 16 fp16 in the 32-byte-swizzled K-major layout
+    // (16-byte chunk index XOR ((row >> 2) & 1)); logical chunk 0 = [-0.5, -1, -2048, 0, 0, 0, 0, 0], chunk 1 = zeros
+    const int r = (warp - 4) * 32 + lane;
+    uint4* rowp = reinterpret_cast<uint4*>(smem + OFF_NB + r * 32);
+    const uint32_t c01 = (uint32_t)__half_as_ushort(__float2half_rn(-0.5f)) | ((uint32_t)__half_as_ushort(__float2half_rn(-1.f)) << 16);
+    const uint32_t c23 = (uint32_t)__half_as_ushort(__float2half_rn(-2048.f));
+    const int sw = (r >> 2) & 1;
+    rowp[sw] = make_uint4(c01, c23, 0u, 0u);
+    rowp[sw ^ 1] = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+  }
   __syncwarp();                      // barrier.cluster is .aligned: every warp must reach it converged
   ptx::tc_fence_before();
   ptx::cluster_sync_all();          // barriers of BOTH CTAs are initialised before anyone signals across the pair
@@ -109,15 +134,19 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         const int ntiles = ((int)p.m_i + BN - 1) / BN;
         for (int t = 0; t < ntiles; ++t) {
           ptx::mbar_wait(&db_empty[st], sph ^ 1);
-          ptx::mbar_wait(&nb_empty[st], sph ^ 1);         // released by the epilogue NS tiles ago: never on the critical path
+          if (!AUG) ptx::mbar_wait(&nb_empty[st], sph ^ 1);         // released by the epilogue NS tiles ago: never on the critical path
           ptx::trace_stamp(trace, 0, tt, 0);
-          uint8_t* ds = smem + OFF_DB + st * DBH_BYTES;
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&db_full[st], 2 * DBH_BYTES);
+          uint8_t* ds = smem + OFF_DB + st * STAGE;
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&db_full[st], 2 * STAGE);
           const int drow = t * BN + (int)rank * 128;
           ptx::tma_load_2d_2sm(ds, &vi->tmap128, &db_full[st], 0, drow);
           ptx::tma_load_2d_2sm(ds + 128 * 128, &vi->tmap128, &db_full[st], 64, drow);
-          ptx::mbar_arrive_expect_tx(&nb_full[st], NB_BYTES);
-          ptx::bulk_load_1d(smem + OFF_NB + st * NB_BYTES, vi->nbh + (size_t)t * BN, NB_BYTES, &nb_full[st]);
+          if (AUG) {
+            ptx::tma_load_2d_2sm(ds + DBH_BYTES, &vi->tmap_aug, &db_full[st], 0, drow);
+          } else {
+            ptx::mbar_arrive_expect_tx(&nb_full[st], NB_BYTES);
+            ptx::bulk_load_1d(smem + OFF_NB + st * NB_BYTES, vi->nbh + (size_t)t * BN, NB_BYTES, &nb_full[st]);
+          }
           ptx::trace_stamp(trace, 0, tt, 1); ++tt;
           if (++st == NS) { st = 0; sph ^= 1; }
         }
@@ -141,25 +170,25 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           if (!tm_ready) ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
           ptx::trace_stamp(trace, 1, tt, 1);
           ptx::tc_fence_after();
-          const uint32_t a_base = q_addr + qb * Q_BYTES, b_base = db_addr + st * DBH_BYTES, d_addr = tmem_base + ac * BN;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + k * 32), ptx::umma_desc_k_sw128(b_base + k * 32), idesc, k > 0 ? 1u : 0u);
-          // While the tensor pipe chews on the first four MMAs, look at the NEXT tile's barriers: observing a completed
-          // mbarrier costs ~100 cycles, and two of them per tile between commits would idle the pipe.  The database
-          // slot is normally long since full (blocking wait is free); the TMEM stage may not be drained yet, so it is
-          // only polled once here and waited for at the top of the next tile if needed.
+          const uint32_t a_base = q_addr + qb * Q_BYTES, b_base = db_addr + st * STAGE, d_addr = tmem_base + ac * BN;
+          // Observing a completed mbarrier costs ~100 cycles; doing that between the commit of one tile and the first MMA of
+          // the next would idle the tensor pipe.  So the NEXT tile's barriers are polled while this tile's MMAs are queued:
+          // the database slot (full long ago) after the 4th MMA, the TMEM stage (drained by the epilogue ~0.8 tile after its
+          // MMAs retired) as late as possible, before the last two MMAs.  A failed poll falls back to a blocking wait at
+          // the top of the next tile.
           const uint32_t nst = (st + 1 == NS) ? 0 : st + 1, nsph = (st + 1 == NS) ? (sph ^ 1) : sph;
           const uint32_t nac = ac ^ 1, naph = (nac == 0) ? (aph ^ 1) : aph;
+          const bool more = (t + 1 < ntiles);
           db_ready = tm_ready = false;
-          if (t + 1 < ntiles) {
-            db_ready = ptx::mbar_try_wait(&db_full[nst], nsph);
-            tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
-          }
 #pragma unroll
-          for (int k = 4; k < 8; ++k)
-            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + (BM * 128) + (k & 3) * 32),
-                                 ptx::umma_desc_k_sw128(b_base + (128 * 128) + (k & 3) * 32), idesc, 1u);
+          for (int k = 0; k < 8; ++k) {
+            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32),
+                                 ptx::umma_desc_k_sw128(b_base + (k >> 2) * (128 * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u);
+            if (k == 3 && more) db_ready = ptx::mbar_try_wait(&db_full[nst], nsph);
+            if (k == (AUG ? 6 : 5) && more) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+          }
+          if (AUG)   // 9th K-step: constants x half-norm limbs
+            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB)), ptx::umma_desc_k_sw32(b_base + DBH_BYTES), idesc, 1u);
           ptx::umma_commit_2sm_mc(&db_empty[st], 3);
           ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
           ptx::trace_stamp(trace, 1, tt, 2); ++tt;
@@ -212,7 +241,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       const int ntiles = ((int)p.m_i + BN - 1) / BN;
       tc::Top2 s{INFINITY, INFINITY, 0u};
       for (int t = 0; t < ntiles; ++t) {
-        if (t == 0) ptx::mbar_wait(&nb_full[st], sph);     // later tiles: already observed at the end of the previous tile
+        if (!AUG && t == 0) ptx::mbar_wait(&nb_full[st], sph);     // later tiles: already observed at the end of the previous tile
         ptx::trace_stamp(etrace, 2 + colq, tt, 0);
         ptx::mbar_wait(&tm_full[ac], aph);
         ptx::trace_stamp(etrace, 2 + colq, tt, 1);
@@ -231,7 +260,12 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           if (c + 1 < COLS / 32) ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, nxt);
           if (dbg == 0) {
             float h[32];
-            tc::add_halfnorms(cur, nb4 + c * 8, h);
+            if (AUG) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) h[e] = __uint_as_float(cur[e]);     // the accumulator already is h
+            } else {
+              tc::add_halfnorms(cur, nb4 + c * 8, h);
+            }
             tc::fold_chunk(h, gbase + c * 2, s);
             tc::fold_chunk(h + 16, gbase + c * 2 + 1, s);
           } else {
@@ -247,14 +281,14 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          ptx::mbar_arrive(&nb_empty[st]);                // local: the half-norm buffer may be overwritten
+          if (!AUG) ptx::mbar_arrive(&nb_empty[st]);      // local: the half-norm buffer may be overwritten
           ptx::mbar_arrive_cluster(&tm_empty[ac], 0);     // leader: this CTA's rows of TMEM stage ac are drained
         }
         ac ^= 1; if (ac == 0) aph ^= 1;
         if (++st == NS) { st = 0; sph ^= 1; }
         // the next tile's half-norms landed long ago; observing their barrier now (while the tensor pipe is still busy with
         // that tile) takes ~100 cycles off the serial MMA -> epilogue -> MMA chain
-        if (t + 1 < ntiles) ptx::mbar_wait(&nb_full[st], sph);
+        if (!AUG && t + 1 < ntiles) ptx::mbar_wait(&nb_full[st], sph);
       }
       // merge the column groups of each query row, pre-test, emit candidates
       float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * 3 * BM;

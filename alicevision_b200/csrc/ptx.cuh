@@ -104,6 +104,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same for a K-major operand whose rows are 32 bytes (16 fp16) wide with 32-byte swizzle: 8 rows * 32 B = 256 B between
+// row groups, layout = 6 (SWIZZLE_32B).
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16, F16 x F16 -> F32, both operands K-major (InstrDescriptor in the same header):
 //   [4,6) c_format = 1 (F32) | [7,10) a_format = 0 (F16) | [10,13) b_format = 0 | [13] a_negate | [14] b_negate
 //   [15] a_major = 0 (K) | [16] b_major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--images", type=int, default=0, help="0 = 100 per GPU-equivalent (IMAGES_FOR_GPUS)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "u8", "bin"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--tc-variant", type=int, default=2, choices=[1, 2, 3], help="2/3 = CTA-pair tcgen05 kernel with 8/16 epilogue warps, 1 = single-CTA kernel")
+    ap.add_argument("--tc-variant", type=int, default=4, choices=[1, 2, 3, 4], help="4 = CTA-pair tcgen05 kernel, half-norms folded into the GEMM (default); 2/3 = CTA pair with epilogue add (8/16 epilogue warps); 1 = single-CTA kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -271,7 +271,7 @@ def main():
                                "note": "popc-issue bound by construction (M^2*16 popc32 per pair vs 2*M*64 bytes); HBM fraction reported because the north star asks"}
         else:
             out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                               "kernel": ("tc2::l2_top2_tc2_kernel<%d> (cta_group::2)" % (8 if args.tc_variant == 2 else 16)) if args.tc_variant >= 2 else "tc::l2_top2_tc_kernel", "peak_source": peak_src, "flop_per_pair": flop_pair,
+                               "kernel": {1: "tc::l2_top2_tc_kernel", 2: "tc2::l2_top2_tc2_kernel<8,false> (cta_group::2)", 3: "tc2::l2_top2_tc2_kernel<16,false> (cta_group::2)", 4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant], "peak_source": peak_src, "flop_per_pair": flop_pair,
                                "kernel_ms_per_step": ms_search}
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(descs, xys, pairs, hamming, args.cpu_seconds)

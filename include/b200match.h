@@ -58,7 +58,8 @@ void b200m_ctx_destroy(b200m_ctx* ctx);
 int b200m_ctx_set_host_threads(b200m_ctx* ctx, int n);
 /* force every L2 pair through the exact CUDA-core kernels (testing / A-B comparison); default 0 */
 int b200m_ctx_set_force_exact(b200m_ctx* ctx, int on);
-/* tensor-core kernel variant: 2 = CTA-pair (cta_group::2, default), 1 = single CTA (kept for A-B comparison) */
+/* tensor-core kernel variant (A-B comparison): 4 = CTA pair (cta_group::2) with the half-norms folded into the GEMM (default),
+ * 2 / 3 = CTA pair with an add in the epilogue (8 / 16 epilogue warps), 1 = single CTA */
 int b200m_ctx_set_tc_variant(b200m_ctx* ctx, int variant);
 
 /* debug: per-tile SM-clock trace of CTA 0 of the tensor-core kernel (4 roles x 512 tiles x 4 stamps); enable!=0 allocates,

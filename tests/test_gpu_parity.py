@@ -27,7 +27,7 @@ def assert_same(got, want, rtol=0.0):
             assert np.allclose(g["dist"], w["dist"], rtol=rtol, atol=0) and np.allclose(g["ratio"], w["ratio"], rtol=rtol, atol=0)
 
 
-def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False, variant=2):
+def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False, variant=4):
     t = EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200
     m = ImageCollectionMatcherB200(ratio, cross, t)
     m.clear()
@@ -37,7 +37,7 @@ def run(ds, xys, pairs, hamming=False, cross=False, ratio=0.8, force_exact=False
         return m.Match({i: (ds[i], xys[i]) for i in range(len(ds))}, pairs), m
     finally:
         m.ctx.set_force_exact(False)
-        m.ctx.set_tc_variant(2)
+        m.ctx.set_tc_variant(4)
 
 
 # ---------------------------------------------------------------------------------------------- Surface 1
@@ -99,7 +99,7 @@ def test_golden_fixtures_gpu():
                 assert m.ctx.last_tc_pairs() > 0 and m.ctx.exactness_errors() == 0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
 @pytest.mark.parametrize("cross", [False, True])
 def test_collection_tensorcore_vs_oracle(ora, dtype, cross, variant):
@@ -177,7 +177,7 @@ def test_ratio_values(ora):
         assert_same(got, ora.collection_match(descs, xys, [(0, 1)], r))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_full_size_properties(variant):
     """BASELINE config sizes (8192 features): size-independent properties instead of the (slow) oracle.
     1. self-match: every feature's nearest neighbour in its own image is itself (d = 0) -> after the ratio test

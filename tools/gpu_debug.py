@@ -57,7 +57,7 @@ def experiment(name):
     pairs = synth.exhaustive_pairs(sizes[0])
     a = raw(m, pairs, True)
     print("  exact done; launches", m.ctx.last_launches())
-    for variant in (1, 2):
+    for variant in (1, 2, 4):
         b = raw(m, pairs, False, variant=variant)
         print(f"  tc variant {variant} done; tc_pairs", m.ctx.last_tc_pairs(), "exactness_errors", m.ctx.exactness_errors(), "gpu_ms", m.ctx.last_gpu_ms(), "search_ms", m.ctx.last_search_kernel_ms(), flush=True)
         cmp_raw(a, b, f"{name}/v{variant}")

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the dominant kernels (one GPU). Numbers printed under ncu are NOT bench values.
 mkdir -p gpurun_out
-R=${1:-r01b}
+R=${1:-r01c}
 echo "=== launch list (same command as the bench line, short)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/launches_${R}.log 2>&1
