@@ -45,7 +45,9 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             used.insert(p.first);
             used.insert(p.second);
         }
-        std::vector<float> xy;
+        // one bulk upload per element type (the engine pipelines the host->device copies of consecutive views)
+        struct Group { std::vector<uint32_t> ids; std::vector<const void*> descs; std::vector<int> counts; std::vector<std::vector<float>> xy; int dim = 0; };
+        Group groups[3];
         for (IndexT viewId : used)
         {
             const feature::Regions& r = regionsPerView.getRegions(viewId, descType);   // throws like the reference on unknown ids
@@ -59,14 +61,28 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
                 dtype = B200M_U8;
             else
                 continue;   // createRegionsMatcher has no brute-force case for other scalar types on this engine
-            xy.resize(2 * static_cast<size_t>(n));
+            Group& g = groups[dtype];
+            g.dim = static_cast<int>(r.DescriptorLength());
+            g.ids.push_back(viewId);
+            g.descs.push_back(n ? r.DescriptorRawData() : nullptr);
+            g.counts.push_back(n);
+            g.xy.emplace_back(2 * static_cast<size_t>(n));
             const auto& feats = r.Features();
             for (int k = 0; k < n; ++k)
             {
-                xy[2 * k] = feats[k].x();
-                xy[2 * k + 1] = feats[k].y();
+                g.xy.back()[2 * k] = feats[k].x();
+                g.xy.back()[2 * k + 1] = feats[k].y();
             }
-            if (b200m_upload_view(_ctx, viewId, n ? r.DescriptorRawData() : nullptr, n, static_cast<int>(r.DescriptorLength()), dtype, xy.data()) != B200M_OK)
+        }
+        for (int dtype = 0; dtype < 3; ++dtype)
+        {
+            Group& g = groups[dtype];
+            if (g.ids.empty())
+                continue;
+            std::vector<const float*> xyp;
+            for (auto& v : g.xy)
+                xyp.push_back(v.data());
+            if (b200m_upload_views(_ctx, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data()) != B200M_OK)
                 throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
         }
         std::vector<uint32_t> flat;

@@ -15,6 +15,8 @@
 #include "verify.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -132,8 +134,8 @@ struct b200m_ctx {
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
   // upload staging: pageable caller memory -> pinned ring (parallel memcpy on the pool) -> async H2D
-  static constexpr int NSTG = 4;
-  void* stg[NSTG] = {nullptr, nullptr, nullptr, nullptr}; size_t stg_bytes[NSTG] = {0, 0, 0, 0}; cudaEvent_t stg_ev[NSTG] = {nullptr, nullptr, nullptr, nullptr}; int stg_next = 0;
+  static constexpr int NSTG = 6;
+  void* stg[NSTG] = {}; size_t stg_bytes[NSTG] = {}; cudaEvent_t stg_ev[NSTG] = {};
   ViewDev* h_views = nullptr;     // pinned mirror of the device view table (source of the async table updates)
   unsigned int* d_err = nullptr;
   long long* d_trace = nullptr;   // optional pipeline trace of CTA 0 (debug)
@@ -157,48 +159,11 @@ struct b200m_result {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-// Copies caller (pageable) memory to the device through a pinned staging ring; the host-side memcpy is split over the pool.
-static int staged_h2d(b200m_ctx* c, void* dst, const void* src, size_t bytes) {
-  size_t done = 0;
-  const size_t CH = 16u << 20;
-  while (done < bytes) {
-    const size_t n = std::min(CH, bytes - done);
-    const int sidx = c->stg_next; c->stg_next = (c->stg_next + 1) % b200m_ctx::NSTG;
-    if (c->stg_bytes[sidx] < n) {
-      if (c->stg[sidx]) { CK(cudaEventSynchronize(c->stg_ev[sidx])); CK(cudaFreeHost(c->stg[sidx])); c->stg[sidx] = nullptr; }
-      CK(cudaMallocHost(&c->stg[sidx], std::max(n, (size_t)(4u << 20))));
-      c->stg_bytes[sidx] = std::max(n, (size_t)(4u << 20));
-      if (!c->stg_ev[sidx]) CK(cudaEventCreateWithFlags(&c->stg_ev[sidx], cudaEventDisableTiming));
-    } else {
-      CK(cudaEventSynchronize(c->stg_ev[sidx]));     // the previous H2D out of this buffer has completed
-    }
-    char* d = (char*)c->stg[sidx]; const char* sp = (const char*)src + done;
-    const int parts = (int)std::min<size_t>(8, std::max<size_t>(1, n >> 19));
-    if (parts > 1) {
-      std::atomic<int> left{parts};
-      std::mutex mu; std::condition_variable cv;
-      for (int k = 0; k < parts; ++k) {
-        const size_t a = n * k / parts, b = n * (k + 1) / parts;
-        c->pool->submit([=, &left, &mu, &cv] { std::memcpy(d + a, sp + a, b - a); if (--left == 0) { std::lock_guard<std::mutex> l(mu); cv.notify_one(); } });
-      }
-      std::unique_lock<std::mutex> l(mu);
-      cv.wait(l, [&] { return left.load() == 0; });
-    } else {
-      std::memcpy(d, sp, n);
-    }
-    CK(cudaMemcpyAsync((char*)dst + done, d, n, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->stg_ev[sidx], c->stream));
-    done += n;
-  }
-  return B200M_OK;
-}
-
-static int alloc_view_buffers(b200m_ctx* c, ViewHost& v, const void* desc) {
+// Device buffers of one view (stream-ordered allocations out of the default pool).
+static int alloc_view_buffers(b200m_ctx* c, ViewHost& v) {
   const size_t esz = v.dtype == DT_F32 ? 4 : 1;
   const size_t bytes = (size_t)v.m * v.dim * esz;
   CK(cudaMallocAsync(&v.raw, std::max<size_t>(bytes, 256), c->stream));
-  int rc = staged_h2d(c, v.raw, desc, bytes);
-  if (rc) return rc;
   if (v.tc_capable()) {
     v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
     CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
@@ -471,47 +436,127 @@ int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
 }
 
 // ---- Surface 2: views -------------------------------------------------------------------------------------------
-int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy) {
+// Upload of n views in one call.  Caller memory is pageable, so descriptors go through a ring of pinned staging buffers:
+// pool threads memcpy chunk k+1 / k+2 into pinned memory while the copy engine moves chunk k (the H2D of a chunk is
+// issued two chunks behind its memcpy), and each view's preparation kernel follows its last chunk on the stream.
+int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                       const float* const* xys) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
-  if (n < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n > 0 && !desc)) return fail(B200M_ERR_ARG, "bad view arguments");
+  if (n_views < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n_views > 0 && (!view_ids || !descs || !counts))) return fail(B200M_ERR_ARG, "bad view arguments");
+  for (int i = 0; i < n_views; ++i) if (counts[i] < 0 || (counts[i] > 0 && !descs[i])) return fail(B200M_ERR_ARG, "bad view arguments");
   CK(cudaSetDevice(c->device));
-  int slot;
-  auto it = c->slot_of.find(view_id);
-  if (it == c->slot_of.end()) {
-    slot = (int)c->views.size();
-    int rc = ensure_view_capacity(c, slot + 1);
-    if (rc) return rc;
-    c->views.emplace_back();
-    c->slot_of[view_id] = slot;
-  } else {
-    slot = it->second;
-    c->pool->wait();
-    free_view_buffers(c, c->views[slot]);
+  const size_t esz = dtype == DT_F32 ? 4 : 1;
+  std::vector<int> slots(n_views);
+  bool waited = false;
+  const bool timing = getenv("B200M_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  for (int i = 0; i < n_views; ++i) {
+    int slot;
+    auto it = c->slot_of.find(view_ids[i]);
+    if (it == c->slot_of.end()) {
+      slot = (int)c->views.size();
+      int rc = ensure_view_capacity(c, slot + 1);
+      if (rc) return rc;
+      c->views.emplace_back();
+      c->slot_of[view_ids[i]] = slot;
+    } else {
+      slot = it->second;
+      if (!waited) { c->pool->wait(); waited = true; }     // no pool task may still reference a view that is replaced
+      free_view_buffers(c, c->views[slot]);
+    }
+    slots[i] = slot;
+    ViewHost& v = c->views[slot];
+    v = ViewHost();
+    v.id = view_ids[i]; v.m = counts[i]; v.dim = dim; v.dtype = dtype;
+    const int n = counts[i];
+    if (xys && xys[i] && n > 0) {
+      v.xy.assign(xys[i], xys[i] + 2 * (size_t)n);         // checked for general position after the copies (below)
+    }
+    if (n > 0) { int rc = alloc_view_buffers(c, v); if (rc) return rc; }
   }
-  ViewHost& v = c->views[slot];
-  v = ViewHost();
-  v.id = view_id; v.m = n; v.dim = dim; v.dtype = dtype;
-  if (xy && n > 0) {
-    v.xy.assign(xy, xy + 2 * (size_t)n);
-    ViewHost* vp = &v;                                   // deque element: stable address
-    c->pool->submit([vp, n] { vp->generic_pos = positions_generic(vp->xy, n); });   // consumed by the finishing stage only
+  const double t_alloc = now();
+  // ---- chunked, pipelined host -> pinned -> device copies
+  struct Chunk { int view; size_t off, bytes; bool last; };
+  std::vector<Chunk> chunks;
+  const char* e_ch = getenv("B200M_UP_CHUNK_MB"); const char* e_parts = getenv("B200M_UP_PARTS"); const bool direct = getenv("B200M_UP_DIRECT") != nullptr;
+  const size_t CH = (size_t)(e_ch ? atoi(e_ch) : 4) << 20;
+  const int max_parts = e_parts ? atoi(e_parts) : 1;
+  for (int i = 0; i < n_views; ++i) {
+    const size_t bytes = (size_t)counts[i] * dim * esz;
+    for (size_t off = 0; off < bytes; off += CH) chunks.push_back({i, off, std::min(CH, bytes - off), off + CH >= bytes});
   }
-  if (n > 0) {
-    int rc = alloc_view_buffers(c, v, desc);
-    if (rc) return rc;
+  for (int k = 0; k < b200m_ctx::NSTG; ++k) {
+    if (c->stg_bytes[k] < CH) {
+      if (c->stg[k]) { CK(cudaEventSynchronize(c->stg_ev[k])); CK(cudaFreeHost(c->stg[k])); c->stg[k] = nullptr; }
+      CK(cudaMallocHost(&c->stg[k], CH)); c->stg_bytes[k] = CH;
+    }
+    if (!c->stg_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_ev[k], cudaEventDisableTiming));
+  }
+  auto finish_view = [&](int i) -> int {                   // runs right after the last chunk of view i was enqueued
+    ViewHost& v = c->views[slots[i]];
     if (v.tc_capable()) {
-      CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->stream));
-      rc = run_prep(c, v, c->d_flags + slot);
+      CK(cudaMemsetAsync(c->d_flags + slots[i], 0, 4, c->stream));
+      int rc = run_prep(c, v, c->d_flags + slots[i]);
       if (rc) return rc;
       v.flags_known = false;
     }
+    return B200M_OK;
+  };
+  const char* e_lag = getenv("B200M_UP_LAG");
+  const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 2));   // chunks between a memcpy and its H2D
+  std::vector<std::unique_ptr<TaskGroup>> grp(chunks.size());
+  auto issue_h2d = [&](size_t k) -> int {
+    const Chunk& ch = chunks[k];
+    const int sidx = (int)(k % b200m_ctx::NSTG);
+    grp[k]->wait();
+    CK(cudaMemcpyAsync((char*)c->views[slots[ch.view]].raw + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->stg_ev[sidx], c->stream));
+    if (ch.last) return finish_view(ch.view);
+    return B200M_OK;
+  };
+  for (size_t k = 0; k < chunks.size(); ++k) {
+    const Chunk& ch = chunks[k];
+    const int sidx = (int)(k % b200m_ctx::NSTG);
+    CK(cudaEventSynchronize(c->stg_ev[sidx]));             // the H2D that last used this staging buffer is done (no-op when never recorded)
+    grp[k].reset(new TaskGroup());
+    if (direct) {   // experiment: let the driver stage the pageable copy
+      grp[k].reset(new TaskGroup());
+      CK(cudaMemcpyAsync((char*)c->views[slots[ch.view]].raw + ch.off, (const char*)descs[ch.view] + ch.off, ch.bytes, cudaMemcpyHostToDevice, c->stream));
+      if (ch.last) { int rc = finish_view(ch.view); if (rc) return rc; }
+      continue;
+    }
+    const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_parts, ch.bytes >> 19));
+    grp[k]->add(parts);
+    char* d = (char*)c->stg[sidx]; const char* sp = (const char*)descs[ch.view] + ch.off; TaskGroup* g = grp[k].get();
+    for (int q = 0; q < parts; ++q) {
+      const size_t a0 = ch.bytes * q / parts, a1 = ch.bytes * (q + 1) / parts;
+      c->pool->submit([=] { std::memcpy(d + a0, sp + a0, a1 - a0); g->done(); });
+    }
+    if (k >= (size_t)LAG) { int rc = issue_h2d(k - LAG); if (rc) return rc; }
   }
-  int rc = make_view_dev(c, v, c->h_views[slot]);
-  if (rc) return rc;
-  // Descriptors went through the pinned staging ring (the caller's memory is already released); the table entry is
-  // copied out of the pinned mirror, so nothing here needs a stream synchronisation.
-  CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
+  if (direct) CK(cudaStreamSynchronize(c->stream));
+  if (!direct) for (size_t k = chunks.size() >= (size_t)LAG ? chunks.size() - LAG : 0; k < chunks.size(); ++k) { int rc = issue_h2d(k); if (rc) return rc; }
+  const double t_copy = now();
+  // ---- position checks run on the pool behind the copies; only the finishing stage consumes the result
+  for (int i = 0; i < n_views; ++i) {
+    ViewHost* vp = &c->views[slots[i]];                    // deque element: stable address
+    const int n = vp->m;
+    if (!vp->xy.empty()) c->pool->submit([vp, n] { vp->generic_pos = positions_generic(vp->xy, n); });
+  }
+  // ---- device view table (tensor maps are encoded on the host from the device addresses)
+  for (int i = 0; i < n_views; ++i) {
+    int rc = make_view_dev(c, c->views[slots[i]], c->h_views[slots[i]]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->d_views + slots[i], c->h_views + slots[i], sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (timing) { const double t_end = now(); CK(cudaStreamSynchronize(c->stream)); fprintf(stderr, "[b200m] upload_views n=%d: slots+alloc %.2f ms, copies %.2f ms, table %.2f ms, drain %.2f ms\n", n_views, t_alloc - t_begin, t_copy - t_alloc, t_end - t_copy, now() - t_end); }
   return B200M_OK;
+}
+
+int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy) {
+  if (n > 0 && !desc) return fail(B200M_ERR_ARG, "bad view arguments");
+  return b200m_upload_views(c, 1, &view_id, &desc, &n, dim, dtype, xy ? &xy : nullptr);
 }
 
 int b200m_clear_views(b200m_ctx* c) {

@@ -30,7 +30,7 @@ MATCH_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("ratio", np.float32
 # every symbol include/b200match.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
-    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_clear_views",
+    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_clear_views",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
 ]
@@ -234,17 +234,22 @@ class ImageCollectionMatcherB200:
     def upload(self, regionsPerView: dict) -> None:
         """regionsPerView: {viewId: (descriptors[n,dim], positions[n,2] or None)} for ONE descriptor type."""
         lib = self.ctx.lib
+        groups = {}                                   # one bulk call per (dim, element type)
         for vid, (desc, xy) in regionsPerView.items():
             d = np.ascontiguousarray(desc)
-            n = d.shape[0]
             dim = d.shape[1] if d.ndim == 2 else 0
             binary = d.dtype == np.uint8 and self.hamming
-            xyp = None
-            if xy is not None:
-                xya = np.ascontiguousarray(xy, np.float32)
-                xyp = xya.ctypes.data_as(C.c_void_p)
-            _check(lib.b200m_upload_view(self.ctx._h, C.c_uint32(vid), d.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(max(dim, 1)),
-                                         C.c_int(_dtype_code(d, binary)), xyp), "b200m_upload_view")
+            xya = None if xy is None else np.ascontiguousarray(xy, np.float32)
+            groups.setdefault((max(dim, 1), _dtype_code(d, binary)), []).append((vid, d, xya))
+        for (dim, code), items in groups.items():
+            n = len(items)
+            ids = np.array([v for v, _, _ in items], np.uint32)
+            counts = np.array([d.shape[0] for _, d, _ in items], np.int32)
+            dptr = (C.c_void_p * n)(*[d.ctypes.data if d.shape[0] else None for _, d, _ in items])
+            have_xy = any(x is not None for _, _, x in items)
+            xptr = (C.c_void_p * n)(*[(x.ctypes.data if x is not None and x.size else None) for _, _, x in items]) if have_xy else None
+            _check(lib.b200m_upload_views(self.ctx._h, C.c_int(n), ids.ctypes.data_as(C.c_void_p), dptr, counts.ctypes.data_as(C.c_void_p),
+                                          C.c_int(dim), C.c_int(code), xptr), "b200m_upload_views")
 
     def clear(self) -> None:
         _check(self.ctx.lib.b200m_clear_views(self.ctx._h), "b200m_clear_views")

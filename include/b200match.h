@@ -80,6 +80,9 @@ int b200m_knn(b200m_ctx* ctx, const b200m_db* db, const void* query, int nq, int
  * DescriptorLength(), GetRegionsPositions(); feature/Regions.hpp:57-62,158,187).  xy = n x 2 float positions
  * (needed by B200M_STAGE_FULL only; may be NULL otherwise).  n == 0 is allowed (view skipped when matched). */
 int b200m_upload_view(b200m_ctx* ctx, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy);
+/* The same for n views of one descriptor type in one call (the copies of consecutive views are pipelined). */
+int b200m_upload_views(b200m_ctx* ctx, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                       const float* const* xys);
 int b200m_clear_views(b200m_ctx* ctx);
 
 /* Match a list of (I, J) view-id pairs: I = database image, J = query image (RegionsMatcher.hpp:157-158).
