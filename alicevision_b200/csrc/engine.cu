@@ -97,6 +97,38 @@ struct TaskGroup {
   void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [this] { return left == 0; }); }
 };
 
+// Recycles large host blocks (per-batch finishing arenas, result arrays) across calls: a fresh 100 MB allocation costs
+// ~25k page faults on first touch, more than the copy that fills it.  Shared by the context and its results.
+struct Recycler {
+  struct Block { b200m_match* p = nullptr; size_t cap = 0; };
+  std::mutex mu; std::vector<Block> free_blocks;
+  Block take(size_t n) {
+    n = std::max<size_t>(n, 1);
+    {
+      std::lock_guard<std::mutex> l(mu);
+      size_t best = free_blocks.size();
+      for (size_t i = 0; i < free_blocks.size(); ++i)
+        if (free_blocks[i].cap >= n && (best == free_blocks.size() || free_blocks[i].cap < free_blocks[best].cap)) best = i;
+      if (best != free_blocks.size()) { Block b = free_blocks[best]; free_blocks.erase(free_blocks.begin() + best); return b; }
+    }
+    Block b; b.cap = n + n / 8; b.p = static_cast<b200m_match*>(::operator new(b.cap * sizeof(b200m_match)));
+    return b;
+  }
+  void give(Block b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> l(mu);
+    if (free_blocks.size() >= 24) {          // keep the pool bounded: drop the smallest
+      size_t sm = 0;
+      for (size_t i = 1; i < free_blocks.size(); ++i) if (free_blocks[i].cap < free_blocks[sm].cap) sm = i;
+      if (free_blocks[sm].cap < b.cap) std::swap(free_blocks[sm], b);
+      ::operator delete(b.p);
+      return;
+    }
+    free_blocks.push_back(b);
+  }
+  ~Recycler() { for (auto& b : free_blocks) ::operator delete(b.p); }
+};
+
 // ------------------------------------------------------------------------------------------------ data model
 struct ViewHost {
   uint32_t id = 0;
@@ -143,6 +175,7 @@ struct b200m_ctx {
   std::vector<cudaEvent_t> tev;   // search-kernel timing events, reused across calls
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   std::unique_ptr<Pool> pool;
+  std::shared_ptr<Recycler> recycler = std::make_shared<Recycler>();
   bool force_exact = false;
   int tc_variant = 4;             // 1 = single-CTA kernel (l2_tc.cuh); CTA-pair kernel (l2_tc2.cuh): 2 = 8 epilogue warps, 3 = 16 epilogue warps,
                                   // 4 (default) = 8 epilogue warps + half-norms folded into the GEMM (AUG)
@@ -155,7 +188,9 @@ struct b200m_db { b200m_ctx* ctx; ViewHost v; int metric; };
 
 struct b200m_result {
   std::vector<uint32_t> pair_ids; std::vector<int64_t> offsets;
-  std::unique_ptr<b200m_match[]> matches;   // uninitialised storage: filled by parallel copies
+  Recycler::Block matches;                  // uninitialised storage filled by parallel copies; returned to the recycler on free
+  std::shared_ptr<Recycler> recycler;
+  ~b200m_result() { if (recycler) recycler->give(matches); else if (matches.p) ::operator delete(matches.p); }
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -645,7 +680,10 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
 
   const float ratio_sq = dist_ratio * dist_ratio;   // Square(f_dist_ratio) in float, RegionsMatcher.hpp:150 / numeric.hpp:130
   // finishing output: one slot per directed pair in a flat arena (capacity = its record count), filled by pool tasks
-  std::vector<std::unique_ptr<b200m_match[]>> arena(batches.size());   // uninitialised, one block per batch
+  struct ArenaSet {                                                     // uninitialised blocks, one per batch, recycled on exit
+    std::vector<Recycler::Block> b; Recycler* r;
+    ~ArenaSet() { for (auto& x : b) r->give(x); }
+  } arena{std::vector<Recycler::Block>(batches.size()), c->recycler.get()};
   std::vector<b200m_match*> dir_ptr(dir.size(), nullptr);
   std::vector<int> dir_len(dir.size(), 0);
   std::vector<std::unique_ptr<TaskGroup>> groups;
@@ -758,7 +796,7 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
       // finishing tasks (one per directed pair) run behind the GPU: they only have to be done before batch bi+2's records
       // are copied into the same pinned buffer.  The per-pair counts/offsets are copied out of the pinned meta block first,
       // because enqueue(bi+2) overwrites it.
-      arena[bi].reset(new b200m_match[std::max(total, 1)]);
+      arena.b[bi] = c->recycler->take((size_t)std::max(total, 1));
       TaskGroup* grp = groups[bi].get();
       int ntasks = 0;
       for (int p = 0; p < np; ++p) if (dir[B.begin + p].mode != PM_SKIP && bb.h_meta[p] > 0) ++ntasks;
@@ -766,7 +804,7 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
       for (int p = 0; p < np; ++p) {
         const size_t di = B.begin + p;
         const Directed d = dir[di];
-        dir_ptr[di] = arena[bi].get() + bb.h_meta[PAIR_CAP + p];
+        dir_ptr[di] = arena.b[bi].p + bb.h_meta[PAIR_CAP + p];
         const int cnt = bb.h_meta[p];
         if (d.mode == PM_SKIP || cnt == 0) continue;
         const Rec* recs = bb.h_out + bb.h_meta[PAIR_CAP + p];
@@ -821,13 +859,14 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     res->offsets[k + 1] = res->offsets[k] + (stage != B200M_STAGE_DEVICE ? dir_len[k * step] : 0);
   }
   const size_t total_matches = (size_t)res->offsets[fwd.size()];
-  res->matches.reset(new b200m_match[std::max<size_t>(total_matches, 1)]);
+  res->recycler = c->recycler;
+  res->matches = c->recycler->take(total_matches);
   if (total_matches) {
     const size_t CHUNK_PAIRS = 64;
     TaskGroup g; g.add((int)((fwd.size() + CHUNK_PAIRS - 1) / CHUNK_PAIRS));
     for (size_t k0 = 0; k0 < fwd.size(); k0 += CHUNK_PAIRS) {
       const size_t k1 = std::min(fwd.size(), k0 + CHUNK_PAIRS);
-      b200m_match* base = res->matches.get(); const int64_t* offs = res->offsets.data();
+      b200m_match* base = res->matches.p; const int64_t* offs = res->offsets.data();
       b200m_match* const* dp = dir_ptr.data(); const int* dl = dir_len.data(); TaskGroup* gp = &g;
       c->pool->submit([=] {
         for (size_t k = k0; k < k1; ++k) if (dl[k * step] > 0) std::memcpy(base + offs[k], dp[k * step], sizeof(b200m_match) * (size_t)dl[k * step]);
@@ -845,7 +884,7 @@ int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int
   if (!r) return fail(B200M_ERR_ARG, "result is null");
   if (pair_ids) *pair_ids = r->pair_ids.data();
   if (offsets) *offsets = r->offsets.data();
-  if (matches) *matches = r->matches.get();
+  if (matches) *matches = r->matches.p;
   return B200M_OK;
 }
 void b200m_result_free(b200m_result* r) { delete r; }
