@@ -91,6 +91,19 @@ int main()
         for (size_t q = 0; q < 1300; ++q)
             if (dr[2 * q] < dr[2 * q + 1]) CHECK(ir[2 * q]._j == ig[2 * q]._j);
     }
+    // --- the reference's own RegionsMatcher template instantiated on the adaptor (what createRegionsMatcher would build,
+    //     matching/RegionsMatcher.cpp:74-79) must give the same IndMatches as on ArrayMatcher_bruteForce
+    {
+        typedef L2_Vectorized<unsigned char> M;
+        RegionsMatcher<ArrayMatcher_bruteForce<unsigned char, M>> ref(rng, *a, true);
+        RegionsMatcher<ArrayMatcher_b200<unsigned char, M>> gpu(rng, *a, true);
+        IndMatches vr, vg;
+        const bool okr = ref.Match(0.8f, *b, vr), okg = gpu.Match(0.8f, *b, vg);
+        CHECK(okr == okg && vr.size() == vg.size() && !vr.empty());
+        for (size_t k = 0; k < std::min(vr.size(), vg.size()); ++k)
+            CHECK(vr[k]._i == vg[k]._i && vr[k]._j == vg[k]._j && vr[k]._distanceRatio == vg[k]._distanceRatio && vr[k]._distance == vg[k]._distance);
+        std::printf("RegionsMatcher<ArrayMatcher_b200>: %zu matches compared\n", vr.size());
+    }
     // --- full collection Match: adaptor vs RegionsMatcher (reference) incl. cross matching
     SIFT_Regions* c = makeRegions<SIFT_Regions, unsigned char>(900, 3, 0, 90, a);
     RegionsPerView rpv;

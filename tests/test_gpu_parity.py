@@ -217,3 +217,21 @@ def test_cpp_adaptors_against_reference_classes():
         pytest.skip("adaptor_test not built (needs /root/reference at build time)")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ADAPTOR TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_reupload_replaces_view_and_bulk_upload_edge_cases(ora):
+    """b200m_upload_views: replacing an uploaded view (no clear), empty views inside a bulk call, views without positions."""
+    descs, xys = synth.sift_images(3, 520, np.uint8, seed=101, pool_factor=1.0)
+    m = ImageCollectionMatcherB200()
+    m.clear()
+    m.upload({0: (descs[0], xys[0]), 1: (descs[1], xys[1]), 2: (np.zeros((0, 128), np.uint8), np.zeros((0, 2), np.float32))})
+    first = m.Match({}, [(0, 1), (0, 2)])
+    assert_same(first, ora.collection_match([descs[0], descs[1], descs[2][:0]], [xys[0], xys[1], xys[2][:0]], [(0, 1), (0, 2)], 0.8))
+    m.upload({1: (descs[2], xys[2])})                       # replace view 1 in place
+    second = m.Match({}, [(0, 1)])
+    assert_same(second, ora.collection_match([descs[0], descs[2]], [xys[0], xys[2]], [(0, 1)], 0.8))
+    m.upload({5: (descs[1], None)})                         # no positions: fine for RAW, an error for FULL
+    _, off, raw = m.match_uploaded([(0, 5)], matching.STAGE_RAW)
+    assert len(raw) > 0
+    with pytest.raises(matching.B200MatchError):
+        m.match_uploaded([(0, 5)], matching.STAGE_FULL)
