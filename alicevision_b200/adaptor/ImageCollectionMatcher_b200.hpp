@@ -45,7 +45,8 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             used.insert(p.first);
             used.insert(p.second);
         }
-        // one bulk upload per element type (the engine pipelines the host->device copies of consecutive views)
+        // one bulk upload per element type; asynchronous: the copies overlap the search of the first pairs, and the Regions
+        // (owned by regionsPerView) outlive b200m_match_pairs, which returns after the last copy has left host memory
         struct Group { std::vector<uint32_t> ids; std::vector<const void*> descs; std::vector<int> counts; std::vector<std::vector<float>> xy; int dim = 0; };
         Group groups[3];
         for (IndexT viewId : used)
@@ -82,7 +83,7 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             std::vector<const float*> xyp;
             for (auto& v : g.xy)
                 xyp.push_back(v.data());
-            if (b200m_upload_views(_ctx, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data()) != B200M_OK)
+            if (b200m_upload_views_async(_ctx, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data()) != B200M_OK)
                 throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
         }
         std::vector<uint32_t> flat;

@@ -135,10 +135,20 @@ struct ViewHost {
   int m = 0, dim = 0, dtype = 0, m_pad = 0;
   void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr;
   std::vector<float> xy;      // m x 2 positions (host only; used by the finishing stage)
-  bool generic_pos = false;   // all x distinct and all y distinct
   uint32_t flags = 0; bool flags_known = true;
+  uint64_t seq = 0;           // upload order (monotonic per context)
+  bool ready = false;         // copies + preparation kernel complete on the device and flags read back
+  // "all x distinct and all y distinct", decided by the first finishing task that needs it
+  struct PosLazy { std::mutex mu; int state = 0; };
+  std::shared_ptr<PosLazy> pos = std::make_shared<PosLazy>();
+  bool generic_pos() const;
   bool tc_capable() const { return dtype != DT_BIN && dim == 128 && m > 0; }
   bool tc_ok() const { return tc_capable() && flags == 0; }
+};
+
+struct UploadJob {
+  int n_views = 0, dim = 0; size_t esz = 1;
+  std::vector<int> slots; std::vector<const void*> descs; std::vector<int> counts;
 };
 
 struct BatchBuf {
@@ -158,17 +168,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct b200m_ctx {
   int device = 0, num_sms = 148;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, up_stream = nullptr;
   bool own_stream = false;
   EncodeTiledFn encode = nullptr;
   std::deque<ViewHost> views;     // deque: references stay valid while pool tasks (position checks) run
   std::unordered_map<uint32_t, int> slot_of;
+  std::vector<int> free_slots;    // slots of removed views (b200m_remove_view), reused by later uploads
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
   // upload staging: pageable caller memory -> pinned ring (parallel memcpy on the pool) -> async H2D
   static constexpr int NSTG = 6;
   void* stg[NSTG] = {}; size_t stg_bytes[NSTG] = {}; cudaEvent_t stg_ev[NSTG] = {};
   ViewDev* h_views = nullptr;     // pinned mirror of the device view table (source of the async table updates)
+  uint32_t* h_flags = nullptr;    // pinned: per-slot exactness flags, copied back behind each view's preparation kernel
+  std::vector<cudaEvent_t> view_ev;   // per slot: recorded on up_stream when the view is complete on the device
+  cudaEvent_t ev_alloc = nullptr;     // search stream -> upload stream: the view buffers of the current job are allocated
+  // uploader thread (one job at a time, FIFO)
+  std::thread up_thread; std::mutex up_mu; std::condition_variable up_cv;
+  std::deque<UploadJob> up_jobs; bool up_quit = false; int up_active = 0;
+  uint64_t up_issued_seq = 0, next_seq = 0;   // last view whose ready event was recorded / last sequence number handed out
+  int up_rc = 0; std::string up_err;
   unsigned int* d_err = nullptr;
   long long* d_trace = nullptr;   // optional pipeline trace of CTA 0 (debug)
   int dbg_ablate = 0;             // debug-only ablation switch of the CTA-pair kernel (results are WRONG when non-zero)
@@ -243,11 +262,12 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   return B200M_OK;
 }
 
-static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag) {
+static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag, cudaStream_t st) {
+  (void)c;
   if (!v.tc_capable()) return B200M_OK;
   const int grid = (v.m_pad + 7) / 8;
-  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
-  else prep_view_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
+  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
+  else prep_view_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
   CK(cudaGetLastError());
   return B200M_OK;
 }
@@ -258,16 +278,27 @@ static bool positions_generic(const std::vector<float>& xy, int m) {
   std::sort(xs.begin(), xs.end()); std::sort(ys.begin(), ys.end());
   return std::adjacent_find(xs.begin(), xs.end()) == xs.end() && std::adjacent_find(ys.begin(), ys.end()) == ys.end();
 }
+bool ViewHost::generic_pos() const {
+  std::lock_guard<std::mutex> l(pos->mu);
+  if (pos->state == 0) pos->state = (!xy.empty() && positions_generic(xy, m)) ? 2 : 1;
+  return pos->state == 2;
+}
 
 static int ensure_view_capacity(b200m_ctx* c, int need) {
   if (need <= c->view_cap) return B200M_OK;
   int cap = std::max(256, c->view_cap * 2);
   while (cap < need) cap *= 2;
-  ViewDev* nv = nullptr; uint32_t* nf = nullptr; ViewDev* nh = nullptr;
+  ViewDev* nv = nullptr; uint32_t* nf = nullptr; ViewDev* nh = nullptr; uint32_t* nhf = nullptr;
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->up_stream));
   CK(cudaMallocHost((void**)&nh, sizeof(ViewDev) * cap));
   if (c->h_views) { std::memcpy(nh, c->h_views, sizeof(ViewDev) * c->view_cap); cudaFreeHost(c->h_views); }
   c->h_views = nh;
+  CK(cudaMallocHost((void**)&nhf, sizeof(uint32_t) * cap));
+  std::memset(nhf, 0, sizeof(uint32_t) * cap);
+  if (c->h_flags) { std::memcpy(nhf, c->h_flags, sizeof(uint32_t) * c->view_cap); cudaFreeHost(c->h_flags); }
+  c->h_flags = nhf;
+  c->view_ev.resize(cap, nullptr);
   CK(cudaMalloc((void**)&nv, sizeof(ViewDev) * cap));
   CK(cudaMalloc((void**)&nf, sizeof(uint32_t) * cap));
   CK(cudaMemset(nf, 0, sizeof(uint32_t) * cap));
@@ -351,7 +382,7 @@ int finish_directed(const Rec* recs, int n, bool hamming, bool full, const ViewH
   std::sort(out, out + cnt, [](const b200m_match& a, const b200m_match& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
   // IndMatchDecorator::getDeduplicated (IndMatchDecorator.hpp:57-69,84-98)
   const float* xi = vi.xy.data(); const float* xj = vj.xy.data();
-  if (vi.generic_pos) {
+  if (vi.generic_pos()) {
     // All left x distinct and all left y distinct: two matches are "equivalent" iff they share the left feature,
     // the first inserted (smallest j) wins, and the in-order walk is ascending left y.
     int w = 0;
@@ -397,6 +428,8 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   if (stream) { c->stream = (cudaStream_t)stream; }
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -419,7 +452,15 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
 void b200m_ctx_destroy(b200m_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  {
+    std::unique_lock<std::mutex> l(c->up_mu);
+    c->up_cv.wait(l, [c] { return c->up_active == 0; });
+    c->up_quit = true;
+  }
+  c->up_cv.notify_all();
+  if (c->up_thread.joinable()) c->up_thread.join();
   c->pool->wait();
+  cudaStreamSynchronize(c->up_stream);
   cudaStreamSynchronize(c->stream);
   for (auto& v : c->views) free_view_buffers(c, v);
   cudaStreamSynchronize(c->stream);
@@ -433,6 +474,10 @@ void b200m_ctx_destroy(b200m_ctx* c) {
   for (auto& e : c->tev) cudaEventDestroy(e);
   for (int k = 0; k < b200m_ctx::NSTG; ++k) { if (c->stg[k]) cudaFreeHost(c->stg[k]); if (c->stg_ev[k]) cudaEventDestroy(c->stg_ev[k]); }
   if (c->h_views) cudaFreeHost(c->h_views);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  for (auto& e : c->view_ev) if (e) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_alloc);
+  cudaStreamDestroy(c->up_stream);
   if (c->d_trace) cudaFree(c->d_trace);
   cudaFree(c->d_views); cudaFree(c->d_flags); cudaFree(c->d_err);
   cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
@@ -471,54 +516,30 @@ int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
 }
 
 // ---- Surface 2: views -------------------------------------------------------------------------------------------
-// Upload of n views in one call.  Caller memory is pageable, so descriptors go through a ring of pinned staging buffers:
-// pool threads memcpy chunk k+1 / k+2 into pinned memory while the copy engine moves chunk k (the H2D of a chunk is
-// issued two chunks behind its memcpy), and each view's preparation kernel follows its last chunk on the stream.
-int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
-                       const float* const* xys) {
-  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
-  if (n_views < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n_views > 0 && (!view_ids || !descs || !counts))) return fail(B200M_ERR_ARG, "bad view arguments");
-  for (int i = 0; i < n_views; ++i) if (counts[i] < 0 || (counts[i] > 0 && !descs[i])) return fail(B200M_ERR_ARG, "bad view arguments");
+// Uploads run on their own thread and their own stream (`up_stream`): caller memory is pageable, so descriptors go through
+// a ring of pinned staging buffers (pool threads memcpy chunk k+1 / k+2 into pinned memory while the copy engine moves
+// chunk k; the H2D of a chunk is issued two chunks behind its memcpy) and each view's preparation kernel, the copy of its
+// exactness flags to pinned host memory and its "ready" event follow its last chunk.  b200m_match_pairs only waits for the
+// views of the batch it is about to enqueue, so the search kernels of the first pairs run while later views are still
+// being copied (the pair list is processed in order of view arrival when uploads are in flight).
+static void publish_issued(b200m_ctx* c, uint64_t seq) {
+  { std::lock_guard<std::mutex> l(c->up_mu); c->up_issued_seq = std::max(c->up_issued_seq, seq); }
+  c->up_cv.notify_all();
+}
+
+static int run_upload(b200m_ctx* c, const UploadJob& job) {
   CK(cudaSetDevice(c->device));
-  const size_t esz = dtype == DT_F32 ? 4 : 1;
-  std::vector<int> slots(n_views);
-  bool waited = false;
   const bool timing = getenv("B200M_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
-  for (int i = 0; i < n_views; ++i) {
-    int slot;
-    auto it = c->slot_of.find(view_ids[i]);
-    if (it == c->slot_of.end()) {
-      slot = (int)c->views.size();
-      int rc = ensure_view_capacity(c, slot + 1);
-      if (rc) return rc;
-      c->views.emplace_back();
-      c->slot_of[view_ids[i]] = slot;
-    } else {
-      slot = it->second;
-      if (!waited) { c->pool->wait(); waited = true; }     // no pool task may still reference a view that is replaced
-      free_view_buffers(c, c->views[slot]);
-    }
-    slots[i] = slot;
-    ViewHost& v = c->views[slot];
-    v = ViewHost();
-    v.id = view_ids[i]; v.m = counts[i]; v.dim = dim; v.dtype = dtype;
-    const int n = counts[i];
-    if (xys && xys[i] && n > 0) {
-      v.xy.assign(xys[i], xys[i] + 2 * (size_t)n);         // checked for general position after the copies (below)
-    }
-    if (n > 0) { int rc = alloc_view_buffers(c, v); if (rc) return rc; }
-  }
-  const double t_alloc = now();
-  // ---- chunked, pipelined host -> pinned -> device copies
+  CK(cudaStreamWaitEvent(c->up_stream, c->ev_alloc, 0));   // the stream-ordered allocations were made on the search stream
   struct Chunk { int view; size_t off, bytes; bool last; };
   std::vector<Chunk> chunks;
-  const char* e_ch = getenv("B200M_UP_CHUNK_MB"); const char* e_parts = getenv("B200M_UP_PARTS"); const bool direct = getenv("B200M_UP_DIRECT") != nullptr;
-  const size_t CH = (size_t)(e_ch ? atoi(e_ch) : 4) << 20;
-  const int max_parts = e_parts ? atoi(e_parts) : 1;
-  for (int i = 0; i < n_views; ++i) {
-    const size_t bytes = (size_t)counts[i] * dim * esz;
+  const char* e_ch = getenv("B200M_UP_CHUNK_MB");
+  const size_t CH = (size_t)(e_ch ? std::max(1, atoi(e_ch)) : 4) << 20;
+  for (int i = 0; i < job.n_views; ++i) {
+    const size_t bytes = (size_t)job.counts[i] * job.dim * job.esz;
+    if (bytes == 0) chunks.push_back({i, 0, 0, true});      // empty view: only its ready event
     for (size_t off = 0; off < bytes; off += CH) chunks.push_back({i, off, std::min(CH, bytes - off), off + CH >= bytes});
   }
   for (int k = 0; k < b200m_ctx::NSTG; ++k) {
@@ -529,13 +550,16 @@ int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, cons
     if (!c->stg_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_ev[k], cudaEventDisableTiming));
   }
   auto finish_view = [&](int i) -> int {                   // runs right after the last chunk of view i was enqueued
-    ViewHost& v = c->views[slots[i]];
+    const int slot = job.slots[i];
+    ViewHost& v = c->views[slot];
     if (v.tc_capable()) {
-      CK(cudaMemsetAsync(c->d_flags + slots[i], 0, 4, c->stream));
-      int rc = run_prep(c, v, c->d_flags + slots[i]);
+      CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->up_stream));
+      int rc = run_prep(c, v, c->d_flags + slot, c->up_stream);
       if (rc) return rc;
-      v.flags_known = false;
+      CK(cudaMemcpyAsync(c->h_flags + slot, c->d_flags + slot, 4, cudaMemcpyDeviceToHost, c->up_stream));
     }
+    CK(cudaEventRecord(c->view_ev[slot], c->up_stream));
+    publish_issued(c, v.seq);
     return B200M_OK;
   };
   const char* e_lag = getenv("B200M_UP_LAG");
@@ -545,8 +569,10 @@ int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, cons
     const Chunk& ch = chunks[k];
     const int sidx = (int)(k % b200m_ctx::NSTG);
     grp[k]->wait();
-    CK(cudaMemcpyAsync((char*)c->views[slots[ch.view]].raw + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->stg_ev[sidx], c->stream));
+    if (ch.bytes) {
+      CK(cudaMemcpyAsync((char*)c->views[job.slots[ch.view]].raw + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->up_stream));
+      CK(cudaEventRecord(c->stg_ev[sidx], c->up_stream));
+    }
     if (ch.last) return finish_view(ch.view);
     return B200M_OK;
   };
@@ -555,38 +581,138 @@ int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, cons
     const int sidx = (int)(k % b200m_ctx::NSTG);
     CK(cudaEventSynchronize(c->stg_ev[sidx]));             // the H2D that last used this staging buffer is done (no-op when never recorded)
     grp[k].reset(new TaskGroup());
-    if (direct) {   // experiment: let the driver stage the pageable copy
-      grp[k].reset(new TaskGroup());
-      CK(cudaMemcpyAsync((char*)c->views[slots[ch.view]].raw + ch.off, (const char*)descs[ch.view] + ch.off, ch.bytes, cudaMemcpyHostToDevice, c->stream));
-      if (ch.last) { int rc = finish_view(ch.view); if (rc) return rc; }
-      continue;
-    }
-    const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_parts, ch.bytes >> 19));
-    grp[k]->add(parts);
-    char* d = (char*)c->stg[sidx]; const char* sp = (const char*)descs[ch.view] + ch.off; TaskGroup* g = grp[k].get();
-    for (int q = 0; q < parts; ++q) {
-      const size_t a0 = ch.bytes * q / parts, a1 = ch.bytes * (q + 1) / parts;
-      c->pool->submit([=] { std::memcpy(d + a0, sp + a0, a1 - a0); g->done(); });
+    if (ch.bytes) {
+      grp[k]->add(1);
+      char* d = (char*)c->stg[sidx]; const char* sp = (const char*)job.descs[ch.view] + ch.off; TaskGroup* g = grp[k].get();
+      const size_t nb = ch.bytes;
+      c->pool->submit([=] { std::memcpy(d, sp, nb); g->done(); });
     }
     if (k >= (size_t)LAG) { int rc = issue_h2d(k - LAG); if (rc) return rc; }
   }
-  if (direct) CK(cudaStreamSynchronize(c->stream));
-  if (!direct) for (size_t k = chunks.size() >= (size_t)LAG ? chunks.size() - LAG : 0; k < chunks.size(); ++k) { int rc = issue_h2d(k); if (rc) return rc; }
-  const double t_copy = now();
-  // ---- position checks run on the pool behind the copies; only the finishing stage consumes the result
-  for (int i = 0; i < n_views; ++i) {
-    ViewHost* vp = &c->views[slots[i]];                    // deque element: stable address
-    const int n = vp->m;
-    if (!vp->xy.empty()) c->pool->submit([vp, n] { vp->generic_pos = positions_generic(vp->xy, n); });
-  }
-  // ---- device view table (tensor maps are encoded on the host from the device addresses)
-  for (int i = 0; i < n_views; ++i) {
-    int rc = make_view_dev(c, c->views[slots[i]], c->h_views[slots[i]]);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(c->d_views + slots[i], c->h_views + slots[i], sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
-  }
-  if (timing) { const double t_end = now(); CK(cudaStreamSynchronize(c->stream)); fprintf(stderr, "[b200m] upload_views n=%d: slots+alloc %.2f ms, copies %.2f ms, table %.2f ms, drain %.2f ms\n", n_views, t_alloc - t_begin, t_copy - t_alloc, t_end - t_copy, now() - t_end); }
+  for (size_t k = chunks.size() >= (size_t)LAG ? chunks.size() - LAG : 0; k < chunks.size(); ++k) { int rc = issue_h2d(k); if (rc) return rc; }
+  if (timing) { const double t_end = now(); CK(cudaStreamSynchronize(c->up_stream)); fprintf(stderr, "[b200m] upload job n=%d: copies issued in %.2f ms, drain %.2f ms\n", job.n_views, t_end - t_begin, now() - t_end); }
   return B200M_OK;
+}
+
+static void uploader_main(b200m_ctx* c) {
+  for (;;) {
+    UploadJob job;
+    {
+      std::unique_lock<std::mutex> l(c->up_mu);
+      c->up_cv.wait(l, [c] { return c->up_quit || !c->up_jobs.empty(); });
+      if (c->up_jobs.empty()) return;
+      job = std::move(c->up_jobs.front()); c->up_jobs.pop_front();
+    }
+    const int rc = run_upload(c, job);
+    {
+      std::lock_guard<std::mutex> l(c->up_mu);
+      if (rc && !c->up_rc) { c->up_rc = rc; c->up_err = g_err; }
+      --c->up_active;
+    }
+    c->up_cv.notify_all();
+  }
+}
+
+// Blocks until every queued upload has issued all its copies (caller memory is no longer read). Returns the first
+// error an upload hit since the last call.
+static int wait_uploads(b200m_ctx* c) {
+  std::unique_lock<std::mutex> l(c->up_mu);
+  c->up_cv.wait(l, [c] { return c->up_active == 0; });
+  const int rc = c->up_rc;
+  if (rc) { g_err = c->up_err; c->up_rc = 0; }
+  return rc;
+}
+
+// Blocks until the view's copies, preparation kernel and flag copy are COMPLETE on the device; then its exactness flags are known.
+static int ensure_view_ready(b200m_ctx* c, int slot) {
+  ViewHost& v = c->views[slot];
+  if (v.ready) return B200M_OK;
+  {
+    std::unique_lock<std::mutex> l(c->up_mu);
+    c->up_cv.wait(l, [&] { return c->up_issued_seq >= v.seq || c->up_rc != 0 || c->up_active == 0; });
+    if (c->up_rc) { g_err = c->up_err; return c->up_rc; }
+    if (c->up_issued_seq < v.seq) return fail(B200M_ERR_INTERNAL, "view was never uploaded");
+  }
+  CK(cudaEventSynchronize(c->view_ev[slot]));
+  if (!v.flags_known) { v.flags = c->h_flags[slot]; v.flags_known = true; }
+  v.ready = true;
+  return B200M_OK;
+}
+
+int b200m_wait_uploads(b200m_ctx* c) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  return wait_uploads(c);
+}
+
+int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                             const float* const* xys) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  if (n_views < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n_views > 0 && (!view_ids || !descs || !counts))) return fail(B200M_ERR_ARG, "bad view arguments");
+  for (int i = 0; i < n_views; ++i) if (counts[i] < 0 || (counts[i] > 0 && !descs[i])) return fail(B200M_ERR_ARG, "bad view arguments");
+  CK(cudaSetDevice(c->device));
+  int rc = wait_uploads(c);              // one job at a time: slot table, staging ring and view table are not shared between jobs
+  if (rc) return rc;
+  UploadJob job;
+  job.n_views = n_views; job.dim = dim; job.esz = dtype == DT_F32 ? 4 : 1;
+  job.slots.resize(n_views); job.descs.assign(descs, descs + n_views); job.counts.assign(counts, counts + n_views);
+  bool waited = false;
+  for (int i = 0; i < n_views; ++i) {
+    int slot;
+    auto it = c->slot_of.find(view_ids[i]);
+    if (it == c->slot_of.end()) {
+      if (!c->free_slots.empty()) {
+        slot = c->free_slots.back(); c->free_slots.pop_back();
+      } else {
+        slot = (int)c->views.size();
+        if ((rc = ensure_view_capacity(c, slot + 1))) return rc;
+        c->views.emplace_back();
+      }
+      c->slot_of[view_ids[i]] = slot;
+    } else {
+      slot = it->second;
+      if (!waited) {       // no finishing task / copy / preparation kernel may still reference a view that is replaced
+        c->pool->wait(); CK(cudaStreamSynchronize(c->up_stream)); waited = true;
+      }
+      free_view_buffers(c, c->views[slot]);
+    }
+    job.slots[i] = slot;
+    ViewHost& v = c->views[slot];
+    v = ViewHost();
+    v.id = view_ids[i]; v.m = counts[i]; v.dim = dim; v.dtype = dtype;
+    v.seq = ++c->next_seq;
+    v.flags_known = !v.tc_capable();
+    const int n = counts[i];
+    if (xys && xys[i] && n > 0) v.xy.assign(xys[i], xys[i] + 2 * (size_t)n);   // general position is checked lazily by the finishing stage
+    if (n > 0 && (rc = alloc_view_buffers(c, v))) return rc;
+    if (!c->view_ev[slot]) CK(cudaEventCreateWithFlags(&c->view_ev[slot], cudaEventDisableTiming));
+  }
+  // device view table (tensor maps are encoded on the host from the device addresses; valid whatever the upload state)
+  for (int i = 0; i < n_views; ++i) {
+    const int slot = job.slots[i];
+    if ((rc = make_view_dev(c, c->views[slot], c->h_views[slot]))) return rc;
+    CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaEventRecord(c->ev_alloc, c->stream));
+  // general-position checks (2 sorts per view) run on the pool now, in parallel; a finishing task that needs one earlier computes it itself
+  for (int i = 0; i < n_views; ++i) {
+    const ViewHost* vp = &c->views[job.slots[i]];          // deque element: stable address; replaced / removed only after pool->wait()
+    if (!vp->xy.empty()) c->pool->submit([vp] { (void)vp->generic_pos(); });
+  }
+  {
+    std::lock_guard<std::mutex> l(c->up_mu);
+    if (!c->up_thread.joinable()) c->up_thread = std::thread(uploader_main, c);
+    c->up_jobs.push_back(std::move(job));
+    ++c->up_active;
+  }
+  c->up_cv.notify_all();
+  return B200M_OK;
+}
+
+int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                       const float* const* xys) {
+  int rc = b200m_upload_views_async(c, n_views, view_ids, descs, counts, dim, dtype, xys);
+  if (rc) return rc;
+  return wait_uploads(c);
 }
 
 int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, int dim, int dtype, const float* xy) {
@@ -597,37 +723,64 @@ int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, i
 int b200m_clear_views(b200m_ctx* c) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
   CK(cudaSetDevice(c->device));
+  int rc = wait_uploads(c);
+  if (rc) return rc;
   c->pool->wait();
+  CK(cudaStreamSynchronize(c->up_stream));
   for (auto& v : c->views) free_view_buffers(c, v);
-  c->views.clear(); c->slot_of.clear();
+  c->views.clear(); c->slot_of.clear(); c->free_slots.clear();
   CK(cudaStreamSynchronize(c->stream));
+  return B200M_OK;
+}
+
+int b200m_remove_view(b200m_ctx* c, uint32_t view_id) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  auto it = c->slot_of.find(view_id);
+  if (it == c->slot_of.end()) return fail(B200M_ERR_ARG, "unknown view id");
+  CK(cudaSetDevice(c->device));
+  int rc = wait_uploads(c);
+  if (rc) return rc;
+  c->pool->wait();                       // no finishing task may still reference the view
+  CK(cudaStreamSynchronize(c->up_stream));   // its copies / preparation kernel are done before the stream-ordered free on the search stream
+  const int slot = it->second;
+  free_view_buffers(c, c->views[slot]);  // stream-ordered: kernels already enqueued on the context's stream still see the buffers
+  c->views[slot] = ViewHost();
+  c->slot_of.erase(it);
+  c->free_slots.push_back(slot);
   return B200M_OK;
 }
 
 // ---- Surface 2: pairs -------------------------------------------------------------------------------------------
 struct Directed { int slot_i, slot_j; uint32_t mode; int fwd_index; bool reverse; };
 
+static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out);
+
 int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out) {
+  const int rc = match_pairs_impl(c, pairs, n_pairs, dist_ratio, cross, stage, out);
+  if (c) {
+    // asynchronous uploads read caller memory until their copies are issued: that is guaranteed on return, error or not
+    const std::string err = g_err;
+    const int rcu = wait_uploads(c);
+    if (rc) { g_err = err; return rc; }
+    if (rcu) { if (out && *out) { b200m_result_free(*out); *out = nullptr; } return rcu; }
+  }
+  return rc;
+}
+
+static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out) {
   if (!c || !out || n_pairs < 0 || (n_pairs > 0 && !pairs) || stage < 0 || stage > 2) return fail(B200M_ERR_ARG, "bad arguments");
   *out = nullptr;
   CK(cudaSetDevice(c->device));
   int rc = ensure_batch_buffers(c);
   if (rc) return rc;
+  const bool timing = getenv("B200M_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
 
   // PairSet semantics (types.hpp:23): unique, lexicographically ordered.
   std::set<std::pair<uint32_t, uint32_t>> ps;
   for (int k = 0; k < n_pairs; ++k) ps.insert({pairs[2 * k], pairs[2 * k + 1]});
   std::vector<std::pair<uint32_t, uint32_t>> fwd(ps.begin(), ps.end());
-
-  // exactness flags of freshly uploaded views
-  bool need_flags = false;
-  for (auto& v : c->views) need_flags |= !v.flags_known;
-  if (need_flags) {
-    std::vector<uint32_t> hf(c->views.size());
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(hf.data(), c->d_flags, 4 * hf.size(), cudaMemcpyDeviceToHost));
-    for (size_t s = 0; s < c->views.size(); ++s) if (!c->views[s].flags_known) { c->views[s].flags = hf[s]; c->views[s].flags_known = true; }
-  }
 
   const bool do_cross = cross != 0 && stage == B200M_STAGE_FULL;
   std::vector<Directed> dir;
@@ -648,8 +801,7 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
         mode = PM_HAMMING;
       } else {
         if (vi.dim != 128) return fail(B200M_ERR_UNSUPPORTED, "scalar descriptors must have 128 components on the collection surface");
-        if (!c->force_exact && vi.tc_ok() && vj.tc_ok()) { mode = PM_TC; ++tc_pairs; }
-        else mode = vi.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8;
+        mode = PM_TC;      // provisional: resolved to the tensor-core or an exact kernel once both views' exactness flags are known (enqueue)
       }
       if (stage == B200M_STAGE_FULL && mode != PM_SKIP && (vi.xy.empty() || vj.xy.empty()))
         return fail(B200M_ERR_ARG, "B200M_STAGE_FULL needs feature positions for every matched view");
@@ -657,25 +809,43 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     }
   }
 
-  // ---- batching
+  // ---- processing order: PairSet order, or - while uploads are in flight - the order in which the pairs' views arrive
+  const size_t step = do_cross ? 2 : 1;
+  std::vector<uint32_t> seqv;                      // directed-pair indices in processing order
+  bool pending = false;
+  {
+    std::vector<uint32_t> ord(fwd.size());
+    for (size_t k = 0; k < fwd.size(); ++k) ord[k] = (uint32_t)k;
+    for (const Directed& d : dir) if (d.mode != PM_SKIP) pending |= !c->views[d.slot_i].ready || !c->views[d.slot_j].ready;
+    if (pending) {
+      std::vector<uint64_t> key(fwd.size());
+      for (size_t k = 0; k < fwd.size(); ++k) key[k] = std::max(c->views[dir[k * step].slot_i].seq, c->views[dir[k * step].slot_j].seq);
+      std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    }
+    seqv.reserve(dir.size());
+    for (uint32_t k : ord) for (size_t u = 0; u < step; ++u) seqv.push_back((uint32_t)(k * step + u));
+  }
+
+  // ---- batching (over the processing order); while views are still arriving the first batches are short so the GPU starts early
   struct Batch { size_t begin, end; };
   std::vector<Batch> batches;
   {
     size_t b0 = 0; long cand = 0, items = 0;
-    const size_t step = do_cross ? 2 : 1;
-    for (size_t k = 0; k < dir.size(); k += step) {
+    size_t pair_cap = pending ? 64 : (size_t)PAIR_CAP;
+    for (size_t k = 0; k < seqv.size(); k += step) {
       long need_c = 0, need_i = 0;
       for (size_t u = k; u < k + step; ++u) {
-        const int mj = c->views[dir[u].slot_j].m;
+        const int mj = c->views[dir[seqv[u]].slot_j].m;
         if (mj > CAND_CAP) return fail(B200M_ERR_UNSUPPORTED, "view too large for one batch");
         need_c += mj; need_i += (mj + tc::BM - 1) / tc::BM;
       }
-      if (k > b0 && (cand + need_c > CAND_CAP || items + need_i > ITEM_CAP || k - b0 + step > (size_t)PAIR_CAP)) {
+      if (k > b0 && (cand + need_c > CAND_CAP || items + need_i > ITEM_CAP || k - b0 + step > pair_cap)) {
         batches.push_back({b0, k}); b0 = k; cand = 0; items = 0;
+        pair_cap = std::min<size_t>(PAIR_CAP, pair_cap * 2);
       }
       cand += need_c; items += need_i;
     }
-    if (dir.size() > b0) batches.push_back({b0, dir.size()});
+    if (seqv.size() > b0) batches.push_back({b0, seqv.size()});
   }
 
   const float ratio_sq = dist_ratio * dist_ratio;   // Square(f_dist_ratio) in float, RegionsMatcher.hpp:150 / numeric.hpp:130
@@ -692,7 +862,6 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
   int launches = 0;
   int64_t total_records = 0;
-  c->pool->wait();
 
   auto enqueue = [&](size_t bi) -> int {
     const Batch& B = batches[bi];
@@ -701,12 +870,24 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     uint32_t cbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
     // In-kernel exactness pass only when a work item lasts long enough (>= 24 database tiles on average) for two warps to
     // re-score the previous item's candidates behind it; shorter images use the stand-alone exactness kernel.
+    // the views of this batch must be complete on the device; their exactness flags decide tensor-core vs exact kernel
+    for (int p = 0; p < np; ++p) {
+      Directed& d = dir[seqv[B.begin + p]];
+      if (d.mode == PM_SKIP) continue;
+      int r2;
+      if ((r2 = ensure_view_ready(c, d.slot_i)) || (r2 = ensure_view_ready(c, d.slot_j))) return r2;
+      if (d.mode == PM_TC) {
+        const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
+        if (!c->force_exact && vi.tc_ok() && vj.tc_ok()) ++tc_pairs;
+        else d.mode = vi.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8;
+      }
+    }
     long tc_rows = 0, tc_n = 0;
-    for (int p = 0; p < np; ++p) if (dir[B.begin + p].mode == PM_TC) { tc_rows += c->views[dir[B.begin + p].slot_i].m; ++tc_n; }
+    for (int p = 0; p < np; ++p) if (dir[seqv[B.begin + p]].mode == PM_TC) { tc_rows += c->views[dir[seqv[B.begin + p]].slot_i].m; ++tc_n; }
     const bool fused = c->tc_variant >= 2 && tc_n > 0 && tc_rows / tc_n >= 6144;
     bool any_f32 = false, any_u8 = false, any_ham = false;
     for (int p = 0; p < np; ++p) {
-      const Directed& d = dir[B.begin + p];
+      const Directed& d = dir[seqv[B.begin + p]];
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
       // the CTA-pair kernel runs the exactness pass itself: its candidates are final records
       const uint32_t dev_mode = (d.mode == PM_TC && fused) ? (uint32_t)PM_TC_FUSED : d.mode;
@@ -761,6 +942,7 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     return B200M_OK;
   };
 
+  const double t_setup = now();
   CK(cudaEventRecord(c->ev_start, c->stream));
   if (stage == B200M_STAGE_DEVICE) {
     for (size_t bi = 0; bi < batches.size(); ++bi) {
@@ -799,10 +981,10 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
       arena.b[bi] = c->recycler->take((size_t)std::max(total, 1));
       TaskGroup* grp = groups[bi].get();
       int ntasks = 0;
-      for (int p = 0; p < np; ++p) if (dir[B.begin + p].mode != PM_SKIP && bb.h_meta[p] > 0) ++ntasks;
+      for (int p = 0; p < np; ++p) if (dir[seqv[B.begin + p]].mode != PM_SKIP && bb.h_meta[p] > 0) ++ntasks;
       grp->add(ntasks);
       for (int p = 0; p < np; ++p) {
-        const size_t di = B.begin + p;
+        const size_t di = seqv[B.begin + p];
         const Directed d = dir[di];
         dir_ptr[di] = arena.b[bi].p + bb.h_meta[PAIR_CAP + p];
         const int cnt = bb.h_meta[p];
@@ -815,9 +997,12 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
         c->pool->submit([=] { *len = finish_directed(recs, cnt, ham, full, *vi, *vj, dst); grp->done(); });
       }
     }
+    const double t_loop = now();
     for (auto& g : groups) g->wait();
+    if (timing) fprintf(stderr, "[b200m] match_pairs: batch loop %.2f ms, last finishing groups +%.2f ms\n", t_loop - t_setup, now() - t_loop);
     if (batches.empty()) CK(cudaEventRecord(c->ev_end, c->stream));
   }
+  const double t_gpu_done = now();
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_end));
@@ -833,7 +1018,6 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
   std::unique_ptr<b200m_result> res(new b200m_result());
   res->pair_ids.reserve(2 * fwd.size());
   res->offsets.assign(fwd.size() + 1, 0);
-  const size_t step = do_cross ? 2 : 1;
   if (stage != B200M_STAGE_DEVICE && do_cross) {
     // keep m iff (m.j, m.i) is in the reverse list (ImageCollectionMatcher_generic.cpp:92-109); filtered in place, in parallel
     TaskGroup g; g.add((int)fwd.size());
@@ -875,6 +1059,8 @@ int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float di
     }
     g.wait();
   }
+  if (timing) fprintf(stderr, "[b200m] match_pairs n=%d stage=%d: setup %.2f ms, batches %.2f ms (gpu %.2f), tail (cross+assemble) %.2f ms, total %.2f ms\n",
+                      n_pairs, stage, t_setup - t_begin, t_gpu_done - t_setup, c->last_gpu_ms, now() - t_gpu_done, now() - t_begin);
   *out = res.release();
   return B200M_OK;
 }

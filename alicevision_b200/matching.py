@@ -12,8 +12,10 @@ Nothing here computes distances: if the CUDA library is missing or no GPU is pre
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 from enum import IntEnum
 
 import numpy as np
@@ -30,7 +32,7 @@ MATCH_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("ratio", np.float32
 # every symbol include/b200match.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
-    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_clear_views",
+    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
 ]
@@ -86,6 +88,20 @@ def _dtype_code(a: np.ndarray, binary: bool) -> int:
     raise TypeError(f"unsupported descriptor dtype {a.dtype} (float32 / uint8 only)")
 
 
+_live_contexts: "weakref.WeakSet[Context]" = weakref.WeakSet()
+
+
+@atexit.register
+def _drain_uploads_at_exit() -> None:
+    """Asynchronous uploads read numpy memory from an engine thread: let them finish before the interpreter frees it."""
+    for ctx in list(_live_contexts):
+        try:
+            if ctx._h:
+                ctx.lib.b200m_wait_uploads(ctx._h)
+        except Exception:
+            pass
+
+
 class Context:
     """One engine instance bound to one GPU (``b200m_ctx``)."""
 
@@ -93,6 +109,7 @@ class Context:
         self.lib = load_library()
         self._h = C.c_void_p()
         _check(self.lib.b200m_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h)), "b200m_ctx_create")
+        _live_contexts.add(self)
 
     def close(self) -> None:
         if self._h:
@@ -230,9 +247,12 @@ class ImageCollectionMatcherB200:
         self.ctx = ctx or default_context()
         self.distRatio, self.crossMatching, self.matcherType = float(distRatio), bool(crossMatching), matcherType
         self.hamming = matcherType in (EMatcherType.BRUTE_FORCE_HAMMING_B200, EMatcherType.BRUTE_FORCE_HAMMING)
+        self._keepalive = []      # descriptor arrays of asynchronous uploads still in flight
 
     def upload(self, regionsPerView: dict) -> None:
-        """regionsPerView: {viewId: (descriptors[n,dim], positions[n,2] or None)} for ONE descriptor type."""
+        """regionsPerView: {viewId: (descriptors[n,dim], positions[n,2] or None)} for ONE descriptor type.
+        Asynchronous (b200m_upload_views_async): the copies overlap the first batches of the next match call; the
+        descriptor arrays are kept alive here until that call (or clear / wait_uploads) returns."""
         lib = self.ctx.lib
         groups = {}                                   # one bulk call per (dim, element type)
         for vid, (desc, xy) in regionsPerView.items():
@@ -248,19 +268,32 @@ class ImageCollectionMatcherB200:
             dptr = (C.c_void_p * n)(*[d.ctypes.data if d.shape[0] else None for _, d, _ in items])
             have_xy = any(x is not None for _, _, x in items)
             xptr = (C.c_void_p * n)(*[(x.ctypes.data if x is not None and x.size else None) for _, _, x in items]) if have_xy else None
-            _check(lib.b200m_upload_views(self.ctx._h, C.c_int(n), ids.ctypes.data_as(C.c_void_p), dptr, counts.ctypes.data_as(C.c_void_p),
-                                          C.c_int(dim), C.c_int(code), xptr), "b200m_upload_views")
+            self._keepalive.append(items)
+            _check(lib.b200m_upload_views_async(self.ctx._h, C.c_int(n), ids.ctypes.data_as(C.c_void_p), dptr, counts.ctypes.data_as(C.c_void_p),
+                                                C.c_int(dim), C.c_int(code), xptr), "b200m_upload_views_async")
+
+    def wait_uploads(self) -> None:
+        try:
+            _check(self.ctx.lib.b200m_wait_uploads(self.ctx._h), "b200m_wait_uploads")
+        finally:
+            self._keepalive.clear()
 
     def clear(self) -> None:
-        _check(self.ctx.lib.b200m_clear_views(self.ctx._h), "b200m_clear_views")
+        try:
+            _check(self.ctx.lib.b200m_clear_views(self.ctx._h), "b200m_clear_views")
+        finally:
+            self._keepalive.clear()
 
     def match_uploaded(self, pairs, stage: int = STAGE_FULL):
         """Runs b200m_match_pairs on already-uploaded views. Returns (pair_ids[n,2], offsets[n+1], matches[MATCH_DTYPE])."""
         lib = self.ctx.lib
         p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         res = C.c_void_p()
-        _check(lib.b200m_match_pairs(self.ctx._h, p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_float(self.distRatio),
-                                     C.c_int(int(self.crossMatching)), C.c_int(stage), C.byref(res)), "b200m_match_pairs")
+        try:
+            _check(lib.b200m_match_pairs(self.ctx._h, p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_float(self.distRatio),
+                                         C.c_int(int(self.crossMatching)), C.c_int(stage), C.byref(res)), "b200m_match_pairs")
+        finally:
+            self._keepalive.clear()      # b200m_match_pairs returns after every pending upload has left caller memory
         owner = _ResultOwner(lib, res)      # the numpy arrays below alias the result's memory; it is freed when they die
         n = lib.b200m_result_num_pairs(res)
         pid, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -276,13 +309,138 @@ class ImageCollectionMatcherB200:
         out = {} if map_PutativesMatches is None else map_PutativesMatches
         self.upload(regionsPerView)
         pair_ids, offsets, matches = self.match_uploaded(pairs, STAGE_FULL)
-        for k in range(pair_ids.shape[0]):
-            a, b = int(offsets[k]), int(offsets[k + 1])
+        offs = offsets.tolist()
+        for (i, j), a, b in zip(pair_ids.tolist(), offs[:-1], offs[1:]):
             if b > a:
-                out[(int(pair_ids[k, 0]), int(pair_ids[k, 1]))] = matches[a:b]     # view into the engine's result arena
+                out[(i, j)] = matches[a:b]     # view into the engine's result arena
         return out
 
 
 def createImageCollectionMatcher(matcherType: EMatcherType, distRatio: float, crossMatching: bool, ctx: Context | None = None):
     """matchingImageCollection/matchingCommon.cpp:19-47 restricted to the matcher types this engine implements."""
     return ImageCollectionMatcherB200(distRatio, crossMatching, matcherType, ctx)
+
+
+# ---- Surface 1b: IRegionsMatcher / RegionsDatabaseMatcher / DistanceRatioMatch ----------------------------------------
+_next_view_id = [0x40000000]
+
+
+def _new_view_id() -> int:
+    _next_view_id[0] += 1
+    return _next_view_id[0]
+
+
+class Regions:
+    """The slice of feature::Regions the matchers read (feature/Regions.hpp:46-118): descriptors[n, L], positions[n, 2],
+    IsBinary().  ``binary`` distinguishes AKAZE_BinaryRegions (uchar[64] bit strings) from SIFT_Regions (uchar[128])."""
+
+    def __init__(self, descriptors: np.ndarray, positions: np.ndarray | None = None, binary: bool = False):
+        self.descriptors = np.ascontiguousarray(descriptors)
+        if self.descriptors.ndim != 2:
+            raise ValueError("descriptors must be [n, L]")
+        n = self.descriptors.shape[0]
+        self.positions = np.zeros((n, 2), np.float32) if positions is None else np.ascontiguousarray(positions, np.float32).reshape(n, 2)
+        self.binary = bool(binary)
+
+    def RegionCount(self) -> int: return int(self.descriptors.shape[0])
+    def DescriptorLength(self) -> int: return int(self.descriptors.shape[1])
+    def IsBinary(self) -> bool: return self.binary
+    def IsScalar(self) -> bool: return not self.binary
+    def Type_id(self) -> str: return "f" if self.descriptors.dtype == np.float32 else "h"
+
+
+class RegionsMatcherB200:
+    """IRegionsMatcher (matching/RegionsMatcher.hpp:49-78) on the engine: the database Regions are uploaded once by the
+    constructor, Match(f_dist_ratio, query_regions) runs RegionsMatcher::Match (:126-176) for that pair on the GPU and
+    returns (ok, matches[MATCH_DTYPE]); ok == "the list is not empty" as in the reference (:175)."""
+
+    def __init__(self, regions: Regions, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.regions_ = regions
+        self._code = _dtype_code(regions.descriptors, regions.binary)
+        self._id = None
+        if regions.RegionCount() > 0:
+            self._id = _new_view_id()
+            self._upload(self._id, regions)
+
+    def _upload(self, vid: int, r: Regions) -> None:
+        n = r.RegionCount()
+        _check(self.ctx.lib.b200m_upload_view(self.ctx._h, C.c_uint32(vid), r.descriptors.ctypes.data_as(C.c_void_p) if n else None, C.c_int(n),
+                                              C.c_int(max(r.DescriptorLength(), 1)), C.c_int(self._code),
+                                              r.positions.ctypes.data_as(C.c_void_p) if n else None), "b200m_upload_view")
+
+    def getDatabaseRegions(self) -> Regions:
+        return self.regions_
+
+    def Match(self, f_dist_ratio: float, query_regions: Regions):
+        empty = np.zeros(0, MATCH_DTYPE)
+        if query_regions.RegionCount() == 0 or self._id is None:
+            return False, empty
+        if (query_regions.descriptors.dtype != self.regions_.descriptors.dtype or query_regions.binary != self.regions_.binary
+                or query_regions.DescriptorLength() != self.regions_.DescriptorLength()):
+            return False, empty
+        lib = self.ctx.lib
+        qid = _new_view_id()
+        self._upload(qid, query_regions)
+        try:
+            pair = np.array([[self._id, qid]], np.uint32)
+            res = C.c_void_p()
+            _check(lib.b200m_match_pairs(self.ctx._h, pair.ctypes.data_as(C.c_void_p), C.c_int(1), C.c_float(f_dist_ratio), C.c_int(0),
+                                         C.c_int(STAGE_FULL), C.byref(res)), "b200m_match_pairs")
+            owner = _ResultOwner(lib, res)
+            off, mat = C.c_void_p(), C.c_void_p()
+            _check(lib.b200m_result_get(res, None, C.byref(off), C.byref(mat)), "b200m_result_get")
+            n = int(_alias(off.value, 16, np.int64, owner)[1])
+            matches = _alias(mat.value, n * MATCH_DTYPE.itemsize, MATCH_DTYPE, owner).copy()
+        finally:
+            lib.b200m_remove_view(self.ctx._h, C.c_uint32(qid))
+        return len(matches) > 0, matches
+
+    def close(self) -> None:
+        if self._id is not None and self.ctx._h:
+            self.ctx.lib.b200m_remove_view(self.ctx._h, C.c_uint32(self._id))
+        self._id = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def createRegionsMatcher(regions: Regions, matcherType: EMatcherType, ctx: Context | None = None):
+    """matching/RegionsMatcher.cpp:54-176 for the matcher types this engine implements.  Invalid requests return None
+    like the reference's null unique_ptr (:61-64): scalar regions + Hamming matcher, binary regions + L2 matcher."""
+    hamming = matcherType in (EMatcherType.BRUTE_FORCE_HAMMING, EMatcherType.BRUTE_FORCE_HAMMING_B200)
+    if matcherType not in (EMatcherType.BRUTE_FORCE_L2, EMatcherType.BRUTE_FORCE_L2_B200) and not hamming:
+        return None
+    if regions.IsScalar() and hamming:
+        return None
+    if regions.IsBinary() and not hamming:
+        return None
+    if regions.descriptors.dtype not in (np.float32, np.uint8):
+        return None
+    return RegionsMatcherB200(regions, ctx)
+
+
+class RegionsDatabaseMatcherB200:
+    """matching::RegionsDatabaseMatcher (RegionsMatcher.hpp:183-220, RegionsMatcher.cpp:30-52)."""
+
+    def __init__(self, matcherType: EMatcherType = EMatcherType.BRUTE_FORCE_L2_B200, database_regions: Regions | None = None, ctx: Context | None = None):
+        self._matcherType = matcherType
+        self._regionsMatcher = None if database_regions is None else createRegionsMatcher(database_regions, matcherType, ctx)
+
+    def Match(self, distRatio: float, queryRegions: Regions):
+        if queryRegions.RegionCount() == 0 or self._regionsMatcher is None:      # RegionsMatcher.cpp:32-38
+            return False, np.zeros(0, MATCH_DTYPE)
+        return self._regionsMatcher.Match(distRatio, queryRegions)
+
+    def getDatabaseRegions(self) -> Regions:
+        return self._regionsMatcher.getDatabaseRegions()
+
+
+def DistanceRatioMatch(f_dist_ratio: float, eMatcherType: EMatcherType, regions_I: Regions, regions_J: Regions, ctx: Context | None = None) -> np.ndarray:
+    """matching::DistanceRatioMatch (RegionsMatcher.cpp:19-28): regions_I = database, regions_J = query."""
+    matcher = RegionsDatabaseMatcherB200(eMatcherType, regions_I, ctx)
+    _, matches = matcher.Match(f_dist_ratio, regions_J)
+    return matches

@@ -83,7 +83,19 @@ int b200m_upload_view(b200m_ctx* ctx, uint32_t view_id, const void* desc, int n,
 /* The same for n views of one descriptor type in one call (the copies of consecutive views are pipelined). */
 int b200m_upload_views(b200m_ctx* ctx, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
                        const float* const* xys);
+/* Asynchronous form: returns once the views are registered; the descriptor copies run on an upload thread and stream
+ * behind the call.  `descs` must stay valid until the next b200m_match_pairs, b200m_wait_uploads, b200m_upload_view(s),
+ * b200m_clear_views or b200m_remove_view on this context RETURNS (positions are copied before returning).
+ * b200m_match_pairs waits only for the views of the batch it is about to enqueue and processes the pair list in the order
+ * the views arrive, so searching overlaps the host->device copies. */
+int b200m_upload_views_async(b200m_ctx* ctx, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim,
+                             int dtype, const float* const* xys);
+/* Block until no upload reads caller memory any more; returns the first error an asynchronous upload hit. */
+int b200m_wait_uploads(b200m_ctx* ctx);
 int b200m_clear_views(b200m_ctx* ctx);
+/* Drop one view (device buffers are released in stream order); unknown id -> B200M_ERR_ARG.  Used by the IRegionsMatcher
+ * adaptor (matching/RegionsMatcher.hpp:49-78), whose database and query regions live only as long as the matcher / the call. */
+int b200m_remove_view(b200m_ctx* ctx, uint32_t view_id);
 
 /* Match a list of (I, J) view-id pairs: I = database image, J = query image (RegionsMatcher.hpp:157-158).
  * dist_ratio as given on the CLI (main_featureMatching.cpp:102): squared internally for L2, used as is for Hamming.

@@ -7,6 +7,7 @@
 
 #include <ArrayMatcher_b200.hpp>
 #include <ImageCollectionMatcher_b200.hpp>
+#include <RegionsMatcher_b200.hpp>
 
 #include <cstdio>
 #include <random>
@@ -151,6 +152,61 @@ int main()
                 CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j && w[k]._distanceRatio == g[k]._distanceRatio && w[k]._distance == g[k]._distance);
         }
         std::printf("collection cross=%d: %zu pairs compared\n", cross, want.size());
+    }
+    // --- IRegionsMatcher adaptor (what createRegionsMatcher returns for the new enum values) vs the reference's
+    //     RegionsMatcher<ArrayMatcher_bruteForce<...>>: one database, several queries, uchar / float / binary, factory rules
+    {
+        typedef ArrayMatcher_bruteForce<unsigned char, L2_Vectorized<unsigned char>> MatcherT;
+        RegionsMatcher<MatcherT> ref(rng, *a, true);
+        std::unique_ptr<IRegionsMatcher> gpu = createRegionsMatcher_b200(rng, *a, false);
+        CHECK(gpu != nullptr);
+        CHECK(createRegionsMatcher_b200(rng, *a, true) == nullptr);   // scalar regions + Hamming matcher: RegionsMatcher.cpp:61-62
+        size_t compared = 0;
+        for (const SIFT_Regions* q : {b, c})
+        {
+            IndMatches vr, vg;
+            const bool okr = ref.Match(0.8f, *q, vr), okg = gpu && gpu->Match(0.8f, *q, vg);
+            CHECK(okr == okg && vr.size() == vg.size() && !vr.empty());
+            for (size_t k = 0; k < std::min(vr.size(), vg.size()); ++k)
+                CHECK(vr[k]._i == vg[k]._i && vr[k]._j == vg[k]._j && vr[k]._distanceRatio == vg[k]._distanceRatio && vr[k]._distance == vg[k]._distance);
+            compared += vr.size();
+        }
+        SIFT_Regions empty;
+        IndMatches ve;
+        CHECK(gpu && !gpu->Match(0.8f, empty, ve) && ve.empty());
+        std::unique_ptr<IRegionsMatcher> gpuEmptyDb = createRegionsMatcher_b200(rng, empty, false);
+        CHECK(gpuEmptyDb && !gpuEmptyDb->Match(0.8f, *b, ve) && ve.empty());
+        CHECK(gpu && &gpu->getDatabaseRegions() == static_cast<const Regions*>(a));
+        // float descriptors (integer-valued: tensor-core path)
+        SIFT_Float_Regions* fa = makeRegions<SIFT_Float_Regions, float>(1100, 5, 0, 120, nullptr);
+        SIFT_Float_Regions* fb = makeRegions<SIFT_Float_Regions, float>(1000, 6, 0, 120, fa);
+        {
+            RegionsMatcher<ArrayMatcher_bruteForce<float, L2_Vectorized<float>>> rf(rng, *fa, true);
+            RegionsMatcher_b200 gf(rng, *fa);
+            IndMatches vr, vg;
+            CHECK(rf.Match(0.8f, *fb, vr) == gf.Match(0.8f, *fb, vg) && vr.size() == vg.size() && !vr.empty());
+            for (size_t k = 0; k < std::min(vr.size(), vg.size()); ++k)
+                CHECK(vr[k]._i == vg[k]._i && vr[k]._j == vg[k]._j && vr[k]._distanceRatio == vg[k]._distanceRatio && vr[k]._distance == vg[k]._distance);
+            compared += vr.size();
+            IndMatches vm;
+            CHECK(!gf.Match(0.8f, *b, vm) && vm.empty());              // element type differs from the database's
+        }
+        // binary descriptors (Hamming, ratio not squared)
+        AKAZE_BinaryRegions* ba = makeRegions<AKAZE_BinaryRegions, unsigned char>(900, 7, 0, 255, nullptr);
+        AKAZE_BinaryRegions* bb = makeRegions<AKAZE_BinaryRegions, unsigned char>(800, 8, 0, 255, ba);
+        {
+            RegionsMatcher<ArrayMatcher_bruteForce<unsigned char, Hamming<unsigned char>>> rh(rng, *ba, false);
+            std::unique_ptr<IRegionsMatcher> gh = createRegionsMatcher_b200(rng, *ba, true);
+            CHECK(gh != nullptr && createRegionsMatcher_b200(rng, *ba, false) == nullptr);
+            IndMatches vr, vg;
+            const bool okr = rh.Match(0.8f, *bb, vr), okg = gh && gh->Match(0.8f, *bb, vg);
+            CHECK(okr == okg && vr.size() == vg.size());
+            for (size_t k = 0; k < std::min(vr.size(), vg.size()); ++k)
+                CHECK(vr[k]._i == vg[k]._i && vr[k]._j == vg[k]._j && vr[k]._distanceRatio == vg[k]._distanceRatio && vr[k]._distance == vg[k]._distance);
+            compared += vr.size();
+        }
+        delete fa; delete fb; delete ba; delete bb;
+        std::printf("RegionsMatcher_b200 (IRegionsMatcher): %zu matches compared\n", compared);
     }
     std::printf(g_fail ? "ADAPTOR TEST FAILED (%d)\n" : "ADAPTOR TEST PASSED\n", g_fail);
     return g_fail ? 1 : 0;

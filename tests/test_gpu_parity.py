@@ -235,3 +235,66 @@ def test_reupload_replaces_view_and_bulk_upload_edge_cases(ora):
     assert len(raw) > 0
     with pytest.raises(matching.B200MatchError):
         m.match_uploaded([(0, 5)], matching.STAGE_FULL)
+
+
+# ---------------------------------------------------------------------------------------------- Surface 1b
+@pytest.mark.parametrize("kind", ["u8", "f32", "real", "bin"])
+def test_regions_matcher_vs_oracle(ora, kind):
+    """IRegionsMatcher / RegionsDatabaseMatcher / DistanceRatioMatch mirrors (matching/RegionsMatcher.hpp:49-78,183-220,
+    RegionsMatcher.cpp:19-52): one database, several queries, against RegionsMatcher::Match of the oracle."""
+    from alicevision_b200 import DistanceRatioMatch, Regions, RegionsDatabaseMatcherB200, createRegionsMatcher
+    hamming = kind == "bin"
+    if hamming:
+        descs, xys = synth.mldb_images(3, 777, seed=31)
+    else:
+        descs, xys = synth.sift_images(3, 777, np.uint8 if kind == "u8" else np.float32, seed=31, pool_factor=1.0)
+        if kind == "real":
+            descs = synth.real_valued(descs)
+    t = EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200
+    regs = [Regions(d, x, binary=hamming) for d, x in zip(descs, xys)]
+    db = RegionsDatabaseMatcherB200(t, regs[0])
+    assert db.getDatabaseRegions() is regs[0]
+    for q in (1, 2, 1):                       # the database stays resident across queries
+        ok, got = db.Match(0.8, regs[q])
+        ok_want, want = ora.regions_match(descs[0], xys[0], descs[q], xys[q], 0.8, hamming)
+        assert ok == ok_want and len(want) > 0
+        assert_same({0: got}, {0: want})
+    got = DistanceRatioMatch(0.6, t, regs[1], regs[2])
+    assert_same({0: got}, {0: ora.regions_match(descs[1], xys[1], descs[2], xys[2], 0.6, hamming)[1]})
+    # factory validity rules (RegionsMatcher.cpp:61-64) and the empty cases (RegionsMatcher.cpp:32-38, RegionsMatcher.hpp:109-110)
+    wrong = EMatcherType.BRUTE_FORCE_L2_B200 if hamming else EMatcherType.BRUTE_FORCE_HAMMING_B200
+    assert createRegionsMatcher(regs[0], wrong) is None
+    assert createRegionsMatcher(regs[0], EMatcherType.ANN_L2) is None
+    ok, got = RegionsDatabaseMatcherB200(wrong, regs[0]).Match(0.8, regs[1])
+    assert not ok and len(got) == 0
+    empty = Regions(descs[0][:0], xys[0][:0], binary=hamming)
+    ok, got = db.Match(0.8, empty)
+    assert not ok and len(got) == 0
+    ok, got = RegionsDatabaseMatcherB200(t, empty).Match(0.8, regs[1])
+    assert not ok and len(got) == 0
+    one = Regions(descs[0][:1], xys[0][:1], binary=hamming)       # NN = 2 > rows: SearchNeighbours false (bruteForce.hpp:105)
+    ok, got = RegionsDatabaseMatcherB200(t, one).Match(0.8, regs[1])
+    assert not ok and len(got) == 0
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_async_upload_overlaps_and_keeps_pairset_order(ora, cross):
+    """b200m_upload_views_async + b200m_match_pairs: the pair list is processed in order of view arrival (several short
+    batches while copies are in flight) but reported in PairSet order with the reference's results; a second call on the
+    now-resident views (natural order, one batch) returns the same lists."""
+    n = 13
+    descs, xys = synth.sift_images(n, 640, np.uint8, seed=77, pool_factor=1.0)
+    descs[5] = descs[5][:0]; xys[5] = xys[5][:0]                       # an empty view in the middle of the upload
+    pairs = synth.exhaustive_pairs(n)[::-1]                            # given in reverse: PairSet semantics sort them
+    m = ImageCollectionMatcherB200(0.8, cross)
+    m.clear()
+    views = {i: (descs[i], xys[i]) for i in range(n)}
+    m.upload({i: v for i, v in views.items() if i % 2 == 1}); m.upload({i: v for i, v in views.items() if i % 2 == 0})   # two jobs
+    pid, off, mat = m.match_uploaded(pairs)
+    assert [tuple(p) for p in pid.tolist()] == sorted(map(tuple, pairs.tolist()))
+    got = {(int(a), int(b)): mat[off[k]:off[k + 1]] for k, (a, b) in enumerate(pid) if off[k + 1] > off[k]}
+    want = ora.collection_match(descs, xys, pairs, 0.8, cross=cross)
+    assert_same(got, want)
+    pid2, off2, mat2 = m.match_uploaded(pairs)
+    assert np.array_equal(pid, pid2) and np.array_equal(off, off2) and np.array_equal(mat, mat2)
+    m.clear()

@@ -1,0 +1,7 @@
+#!/bin/bash
+# Verification of HEAD on a B200 + e2e phase breakdown (B200M_TIMING).
+mkdir -p gpurun_out
+echo "=== pytest"; timeout 1200 python -m pytest tests -m gpu -q --no-header -x 2>&1 | tee gpurun_out/pytest.log | tail -8
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee gpurun_out/smoke.log | tail -3
+echo "=== e2e breakdown"; B200M_TIMING=1 timeout 600 python tools/gpu_e2e_breakdown.py 2>&1 | tee gpurun_out/e2e_breakdown.log | tail -40
+echo "=== bench"; timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tee gpurun_out/bench.log | tail -1 | cut -c1-1500
