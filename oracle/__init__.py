@@ -186,6 +186,49 @@ class Oracle:
         return res
 
 
+    # -- file formats (ref: the reference's own Regions::Save/Load; port: restated stream code) ------------
+    def save_regions(self, desc: np.ndarray, feats: np.ndarray, feat_path: str, desc_path: str, binary: bool = False) -> None:
+        desc = np.ascontiguousarray(desc); feats = np.ascontiguousarray(feats, np.float32).reshape(-1, 4)
+        if self.kind == "ref":
+            r = self.lib.ref_save_regions(C.c_int(_dt(desc, binary)), _p(desc), _p(feats), C.c_int(desc.shape[0]), feat_path.encode(), desc_path.encode())
+            assert r == desc.shape[0], r
+        else:
+            assert self.lib.port_save_feat(feat_path.encode(), _p(feats), C.c_int(feats.shape[0])) == 0
+            assert self.lib.port_save_desc(desc_path.encode(), _p(desc), C.c_long(desc.shape[0]), C.c_int(desc.shape[1] * desc.itemsize)) == 0
+
+    def load_regions(self, feat_path: str, desc_path: str, dtype, dim: int, binary: bool = False, cap: int = 1 << 20):
+        """Returns (descriptors[n, dim], feats[n, 4]); None when the reference throws (missing file)."""
+        desc = np.zeros((cap, dim), dtype); feats = np.zeros((cap, 4), np.float32)
+        if self.kind == "ref":
+            n = self.lib.ref_load_regions(C.c_int(_dt(desc, binary)), feat_path.encode(), desc_path.encode(), _p(desc), _p(feats), C.c_int(cap))
+            if n < 0:
+                return None
+            return desc[:n].copy(), feats[:n].copy()
+        nf = self.lib.port_load_feat(feat_path.encode(), _p(feats), C.c_int(cap))
+        self.lib.port_load_desc.restype = C.c_long
+        nd = self.lib.port_load_desc(desc_path.encode(), _p(desc), C.c_long(cap), C.c_int(dim * desc.itemsize))
+        if nf < 0 or nd < 0:
+            return None
+        return desc[:nd].copy(), feats[:nf].copy()
+
+    def save_matches_txt(self, path: str, blocks) -> None:
+        """blocks: [((I, J), descTypeName, matches[MATCH_DTYPE])] in PairwiseMatches map order (restated: port library)."""
+        lib = C.CDLL(_lib_path("port"))
+        ids = np.array([[b[0][0], b[0][1]] for b in blocks], np.uint32).reshape(-1, 2)
+        names = (C.c_char_p * max(len(blocks), 1))(*[b[1].encode() for b in blocks])
+        offs = np.concatenate([[0], np.cumsum([len(b[2]) for b in blocks])]).astype(np.int64)
+        data = np.concatenate([np.ascontiguousarray(b[2], MATCH_DTYPE) for b in blocks]) if blocks else np.zeros(0, MATCH_DTYPE)
+        assert lib.port_save_matches_txt(path.encode(), C.c_int(len(blocks)), _p(ids), names, _p(offs), _p(data)) == 0
+
+    def load_matches_txt(self, path: str, cap_blocks: int = 1 << 16, cap_matches: int = 1 << 22):
+        lib = C.CDLL(_lib_path("port"))
+        ids = np.zeros((cap_blocks, 2), np.uint32); names = np.zeros((cap_blocks, 32), np.uint8)
+        offs = np.zeros(cap_blocks + 1, np.int64); data = np.zeros(cap_matches, MATCH_DTYPE)
+        nb = lib.port_load_matches_txt(path.encode(), C.c_int(cap_blocks), _p(ids), _p(names), _p(offs), C.c_long(cap_matches), _p(data))
+        assert nb >= 0, nb
+        return [((int(ids[b, 0]), int(ids[b, 1])), bytes(names[b]).split(b"\0")[0].decode(), data[offs[b]:offs[b + 1]].copy()) for b in range(nb)]
+
+
 def best(prefer_ref: bool = True) -> Oracle:
     """The strongest checker available: the compiled reference if its .so exists, else the port."""
     if prefer_ref and available("ref"):

@@ -11,8 +11,11 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <iterator>
 #include <map>
 #include <set>
+#include <string>
 #include <vector>
 #include <omp.h>
 
@@ -250,6 +253,79 @@ int port_collection_match(int dtype, int hamming, int dim, int n_views, const vo
     }
   }
   return visited;
+}
+
+// ---- file formats around the path, restated with the reference's own stream idiom ------------------------------------
+// matches.txt, MatchExporter::saveTxt (matching/io.cpp:281-306): blocks are given in PairwiseMatches map order; every
+// block is one (pair, descType) with its matches; consecutive blocks of the same pair share the "I J\n nbDescType" header.
+int port_save_matches_txt(const char* path, int n_blocks, const uint32_t* pair_ids, const char* const* desc_names, const int64_t* offsets,
+                          const Match* matches) {
+  std::ofstream stream(path, std::ios::out);
+  if (!stream.is_open()) return -1;
+  for (int b = 0; b < n_blocks;) {
+    int e = b;
+    while (e < n_blocks && pair_ids[2 * e] == pair_ids[2 * b] && pair_ids[2 * e + 1] == pair_ids[2 * b + 1]) ++e;
+    const std::size_t I = pair_ids[2 * b], J = pair_ids[2 * b + 1];
+    stream << I << " " << J << '\n' << std::size_t(e - b) << '\n';                    // :295
+    for (int k = b; k < e; ++k) {
+      stream << std::string(desc_names[k]) << " " << std::size_t(offsets[k + 1] - offsets[k]) << '\n';   // :298
+      for (int64_t m = offsets[k]; m < offsets[k + 1]; ++m) stream << matches[m].i << " " << matches[m].j << "\n";   // IndMatch.hpp:67
+    }
+    b = e;
+  }
+  return stream.good() ? 0 : -2;
+}
+// matching::LoadMatchFile (io.cpp:41-71): returns the number of (pair, descType) blocks; outputs are filled up to the caps.
+int port_load_matches_txt(const char* path, int cap_blocks, uint32_t* pair_ids, char* desc_names /* 32 bytes per block */, int64_t* offsets,
+                          long cap_matches, Match* matches) {
+  std::ifstream stream(path);
+  if (!stream.is_open()) return -1;
+  std::size_t I = 0, J = 0, nbDescType = 0;
+  int nb = 0; long nm = 0;
+  offsets[0] = 0;
+  while (stream >> I >> J >> nbDescType) {
+    for (std::size_t i = 0; i < nbDescType; ++i) {
+      std::string descTypeStr; std::size_t nbMatches = 0;
+      stream >> descTypeStr >> nbMatches;
+      if (nb >= cap_blocks || nm + (long)nbMatches > cap_matches) return -2;
+      for (std::size_t k = 0; k < nbMatches; ++k) { Match m{0, 0, 0.f, 0.f}; stream >> m.i >> m.j; matches[nm++] = m; }
+      pair_ids[2 * nb] = (uint32_t)I; pair_ids[2 * nb + 1] = (uint32_t)J;
+      std::strncpy(desc_names + 32 * nb, descTypeStr.c_str(), 31); desc_names[32 * nb + 31] = 0;
+      offsets[++nb] = nm;
+    }
+  }
+  return nb;
+}
+// .feat, saveFeatsToFile / loadFeatsFromFile (feature/PointFeature.hpp:78-122)
+int port_save_feat(const char* path, const float* feats, int n) {
+  std::ofstream file(path);
+  if (!file.is_open()) return -1;
+  for (int i = 0; i < n; ++i) file << feats[4 * i] << " " << feats[4 * i + 1] << " " << feats[4 * i + 2] << " " << feats[4 * i + 3] << "\n";
+  return file.good() ? 0 : -2;
+}
+int port_load_feat(const char* path, float* feats, int cap) {
+  std::ifstream in(path);
+  if (!in.is_open()) return -1;
+  int n = 0; float a, b, c, d;
+  while (in >> a >> b >> c >> d) { if (n < cap) { feats[4 * n] = a; feats[4 * n + 1] = b; feats[4 * n + 2] = c; feats[4 * n + 3] = d; } ++n; }
+  return n;
+}
+// .desc, saveDescsToBinFile / loadDescsFromBinFile (feature/Descriptor.hpp:244-307)
+int port_save_desc(const char* path, const void* data, long rows, int row_bytes) {
+  std::ofstream file(path, std::ios::out | std::ios::binary);
+  if (!file.is_open()) return -1;
+  const std::size_t cardDesc = (std::size_t)rows;
+  file.write((const char*)&cardDesc, sizeof(std::size_t));
+  for (long r = 0; r < rows; ++r) file.write((const char*)data + (size_t)r * row_bytes, row_bytes);
+  return file.good() ? 0 : -2;
+}
+long port_load_desc(const char* path, void* out, long cap_rows, int row_bytes) {
+  std::ifstream in(path, std::ios::in | std::ios::binary);
+  if (!in.is_open()) return -1;
+  std::size_t cardDesc = 0;
+  in.read((char*)&cardDesc, sizeof(std::size_t));
+  for (long r = 0; r < (long)cardDesc && r < cap_rows; ++r) in.read((char*)out + (size_t)r * row_bytes, row_bytes);
+  return (long)cardDesc;
 }
 
 }  // extern "C"

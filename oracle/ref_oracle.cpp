@@ -122,6 +122,37 @@ bool db_match(IRegionsMatcher* m, float ratio, const Regions& q, IndMatches& out
 
 }  // namespace
 
+// ---- the reference's own region file IO (feature/Regions.hpp:166-179 -> PointFeature.hpp:88-122, Descriptor.hpp:244-307) ----
+// feats: n x 4 (x, y, scale, orientation).  dtype as above.
+template <class RegionsT, class T>
+static int save_regions_t(const void* desc, const float* feats, int n, const char* featPath, const char* descPath) {
+  RegionsT r;
+  const T* d = static_cast<const T*>(desc);
+  for (int i = 0; i < n; ++i) {
+    r.Features().emplace_back(feats[4 * i], feats[4 * i + 1], feats[4 * i + 2], feats[4 * i + 3]);
+    typename RegionsT::DescriptorT v;
+    for (int k = 0; k < (int)RegionsT::DescriptorT::static_size; ++k) v[k] = d[(size_t)i * RegionsT::DescriptorT::static_size + k];
+    r.Descriptors().push_back(v);
+  }
+  try { r.Save(featPath, descPath); } catch (const std::exception&) { return -1; }
+  return n;
+}
+template <class RegionsT, class T>
+static int load_regions_t(const char* featPath, const char* descPath, void* desc, float* feats, int cap) {
+  RegionsT r;
+  try { r.Load(featPath, descPath); } catch (const std::exception&) { return -1; }
+  const int n = (int)r.RegionCount();
+  const int nf = (int)r.Features().size();
+  T* d = static_cast<T*>(desc);
+  for (int i = 0; i < std::min(n, cap); ++i)
+    for (int k = 0; k < (int)RegionsT::DescriptorT::static_size; ++k) d[(size_t)i * RegionsT::DescriptorT::static_size + k] = r.Descriptors()[i][k];
+  for (int i = 0; i < std::min(nf, cap); ++i) {
+    const auto& f = r.Features()[i];
+    feats[4 * i] = f.x(); feats[4 * i + 1] = f.y(); feats[4 * i + 2] = f.scale(); feats[4 * i + 3] = f.orientation();
+  }
+  return n == nf ? n : -2;
+}
+
 extern "C" {
 
 struct RefMatch { uint32_t i, j; float ratio, dist; };  // == matching::IndMatch (IndMatch.hpp:60-64)
@@ -261,6 +292,24 @@ int ref_collection_match(int dtype, int hamming, int n_views, const void* const*
     }
   }
   return visited;
+}
+
+int ref_save_regions(int dtype, const void* desc, const float* feats, int n, const char* featPath, const char* descPath) {
+  if (dtype == 0) return save_regions_t<SIFT_Float_Regions, float>(desc, feats, n, featPath, descPath);
+  if (dtype == 1) return save_regions_t<SIFT_Regions, unsigned char>(desc, feats, n, featPath, descPath);
+  return save_regions_t<AKAZE_BinaryRegions, unsigned char>(desc, feats, n, featPath, descPath);
+}
+int ref_load_regions(int dtype, const char* featPath, const char* descPath, void* desc, float* feats, int cap) {
+  if (dtype == 0) return load_regions_t<SIFT_Float_Regions, float>(featPath, descPath, desc, feats, cap);
+  if (dtype == 1) return load_regions_t<SIFT_Regions, unsigned char>(featPath, descPath, desc, feats, cap);
+  return load_regions_t<AKAZE_BinaryRegions, unsigned char>(featPath, descPath, desc, feats, cap);
+}
+// loadDescsFromBinFile<DescriptorT, FileDescriptorT> with a type conversion (Descriptor.hpp:221-283): uchar file -> float memory
+int ref_load_desc_u8_as_f32(const char* descPath, float* out, int cap) {
+  std::vector<Descriptor<float, 128>> v;
+  try { loadDescsFromBinFile<Descriptor<float, 128>, Descriptor<unsigned char, 128>>(descPath, v); } catch (const std::exception&) { return -1; }
+  for (int i = 0; i < std::min((int)v.size(), cap); ++i) for (int k = 0; k < 128; ++k) out[(size_t)i * 128 + k] = v[i][k];
+  return (int)v.size();
 }
 
 }  // extern "C"

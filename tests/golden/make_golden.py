@@ -52,5 +52,36 @@ def main():
     print("wrote reference_small.npz", {k: v.shape for k, v in out.items() if k.endswith("matches")})
 
 
+def io_golden():
+    """Region files written AND read back by the reference's own Regions::Save / Load (feature/Regions.hpp:166-179)."""
+    oracle.build(ref=True)
+    R = oracle.Oracle("ref")
+    rng = np.random.default_rng(20260922)
+    n = 40
+    out = {}
+    for what in ("u8", "f32", "bin"):
+        if what == "bin":
+            d = synth.mldb_images(1, n, seed=8)[0][0]
+        else:
+            d = synth.sift_images(1, n, np.uint8 if what == "u8" else np.float32, seed=8, pool_factor=1.0)[0][0]
+        if what == "f32":
+            d = synth.real_valued([d], seed=4)[0]
+        f = np.empty((n, 4), np.float32)
+        f[:, 0] = rng.uniform(0, 6000, n); f[:, 1] = rng.uniform(0, 4000, n); f[:, 2] = rng.uniform(0.5, 300, n); f[:, 3] = rng.uniform(-3.1416, 3.1416, n)
+        f[:6] = np.array([[0, 0, 0, 0], [1, 2, 3, 4], [1e-7, 123456.789, 1e9, -0.0], [0.1, 0.25, 1e-5, 100000.0], [999999.5, 1000000.0, 1234567.0, 3.14159274],
+                          [5e-5, 0.0001, 12345.678, 1e10]], np.float32)
+        fp, dp = os.path.join(HERE, f"io_{what}.feat"), os.path.join(HERE, f"io_{what}.desc")
+        R.save_regions(d, f, fp, dp, binary=what == "bin")
+        rd, rf = R.load_regions(fp, dp, d.dtype, d.shape[1], binary=what == "bin")
+        assert np.array_equal(rd, d)
+        out[f"desc_{what}"], out[f"feat_{what}"], out[f"feat_read_{what}"] = d, f, rf
+    np.savez_compressed(os.path.join(HERE, "io_golden.npz"), **out)
+    print("wrote io_golden.npz and io_{u8,f32,bin}.{feat,desc}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "io":
+        io_golden()
+    else:
+        main()
+        io_golden()

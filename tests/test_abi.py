@@ -11,10 +11,10 @@ from alicevision_b200 import matching
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "b200match.h")).read()
+def header_functions(header="b200match.h", prefix="b200m_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200m_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():
@@ -24,6 +24,11 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200match.h but not exported"
     assert sorted(matching.ABI_SYMBOLS) == names
+    from alicevision_b200 import regions_io
+    io_names = header_functions("b200io.h", "b200io_")
+    assert len(io_names) >= 12 and sorted(regions_io.IO_SYMBOLS) == io_names
+    for n in io_names:
+        assert hasattr(lib, n), f"{n} declared in include/b200io.h but not exported"
 
 
 def test_no_gpu_fails_loudly():
