@@ -29,7 +29,31 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
         if (b200m_ctx_create(device, nullptr, &_ctx) != B200M_OK)
             throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
     }
-    ~ImageCollectionMatcher_b200() override { b200m_ctx_destroy(_ctx); }
+    /// Several GPUs behind one Match call: the pair list is sharded by database image over one engine context per device
+    /// (b200m_multi_match; no collective, pairs are independent).  An empty list means "every visible device".
+    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming, std::vector<int> devices)
+      : _f_dist_ratio(distRatio),
+        _useCrossMatching(crossMatching),
+        _hamming(hamming)
+    {
+        if (devices.empty())
+            for (int d = 0; d < b200m_device_count(); ++d)
+                devices.push_back(d);
+        if (devices.size() == 1)
+        {
+            if (b200m_ctx_create(devices[0], nullptr, &_ctx) != B200M_OK)
+                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+        }
+        else if (b200m_multi_create(devices.data(), static_cast<int>(devices.size()), &_multi) != B200M_OK)
+            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+    }
+    ~ImageCollectionMatcher_b200() override
+    {
+        if (_ctx != nullptr)
+            b200m_ctx_destroy(_ctx);
+        if (_multi != nullptr)
+            b200m_multi_destroy(_multi);
+    }
 
     /// Same contract as ImageCollectionMatcher_generic::Match: appends to map_PutativesMatches, never inserts empty lists,
     /// silently skips empty / type-mismatched views (:59-63,:74-78), unknown view ids throw std::out_of_range (RegionsPerView.hpp:85).
@@ -75,7 +99,39 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
                 g.xy.back()[2 * k + 1] = feats[k].y();
             }
         }
-        for (int dtype = 0; dtype < 3; ++dtype)
+        std::vector<uint32_t> flat;
+        flat.reserve(2 * pairs.size());
+        for (const Pair& p : pairs)
+        {
+            flat.push_back(p.first);
+            flat.push_back(p.second);
+        }
+        b200m_result* res = nullptr;
+        if (_multi != nullptr)
+        {
+            // all views of one descriptor type share one element type (the Regions class of descType); views of another
+            // type would be skipped by the reference as well (:74-78)
+            int dtype = 0;
+            for (int t = 1; t < 3; ++t)
+                if (groups[t].ids.size() > groups[dtype].ids.size())
+                    dtype = t;
+            Group& g = groups[dtype];
+            std::vector<const float*> xyp;
+            for (auto& v : g.xy)
+                xyp.push_back(v.data());
+            std::set<uint32_t> have(g.ids.begin(), g.ids.end());
+            std::vector<uint32_t> usable;
+            for (size_t k = 0; k + 1 < flat.size(); k += 2)
+                if (have.count(flat[k]) && have.count(flat[k + 1]))
+                {
+                    usable.push_back(flat[k]);
+                    usable.push_back(flat[k + 1]);
+                }
+            if (b200m_multi_match(_multi, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data(),
+                                  usable.data(), static_cast<int>(usable.size() / 2), _f_dist_ratio, _useCrossMatching ? 1 : 0, &res) != B200M_OK)
+                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+        }
+        for (int dtype = 0; dtype < 3 && _multi == nullptr; ++dtype)
         {
             Group& g = groups[dtype];
             if (g.ids.empty())
@@ -86,15 +142,8 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             if (b200m_upload_views_async(_ctx, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data()) != B200M_OK)
                 throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
         }
-        std::vector<uint32_t> flat;
-        flat.reserve(2 * pairs.size());
-        for (const Pair& p : pairs)
-        {
-            flat.push_back(p.first);
-            flat.push_back(p.second);
-        }
-        b200m_result* res = nullptr;
-        if (b200m_match_pairs(_ctx, flat.data(), static_cast<int>(pairs.size()), _f_dist_ratio, _useCrossMatching ? 1 : 0, B200M_STAGE_FULL, &res) != B200M_OK)
+        if (_multi == nullptr &&
+            b200m_match_pairs(_ctx, flat.data(), static_cast<int>(pairs.size()), _f_dist_ratio, _useCrossMatching ? 1 : 0, B200M_STAGE_FULL, &res) != B200M_OK)
             throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
         const uint32_t* ids = nullptr;
         const int64_t* off = nullptr;
@@ -119,6 +168,7 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
     bool _useCrossMatching;
     bool _hamming;
     b200m_ctx* _ctx = nullptr;
+    b200m_multi* _multi = nullptr;
 };
 
 }  // namespace matchingImageCollection

@@ -177,7 +177,7 @@ struct b200m_ctx {
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
   // upload staging: pageable caller memory -> pinned ring (parallel memcpy on the pool) -> async H2D
-  static constexpr int NSTG = 6;
+  static constexpr int NSTG = 8;
   void* stg[NSTG] = {}; size_t stg_bytes[NSTG] = {}; cudaEvent_t stg_ev[NSTG] = {};
   ViewDev* h_views = nullptr;     // pinned mirror of the device view table (source of the async table updates)
   uint32_t* h_flags = nullptr;    // pinned: per-slot exactness flags, copied back behind each view's preparation kernel
@@ -535,8 +535,9 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
   CK(cudaStreamWaitEvent(c->up_stream, c->ev_alloc, 0));   // the stream-ordered allocations were made on the search stream
   struct Chunk { int view; size_t off, bytes; bool last; };
   std::vector<Chunk> chunks;
-  const char* e_ch = getenv("B200M_UP_CHUNK_MB");
+  const char* e_ch = getenv("B200M_UP_CHUNK_MB"); const char* e_parts = getenv("B200M_UP_PARTS");
   const size_t CH = (size_t)(e_ch ? std::max(1, atoi(e_ch)) : 4) << 20;
+  const int max_parts = e_parts ? std::max(1, atoi(e_parts)) : 1;   // measured: splitting a chunk over threads is slower (profiles/r01d_upload_staging.md)
   for (int i = 0; i < job.n_views; ++i) {
     const size_t bytes = (size_t)job.counts[i] * job.dim * job.esz;
     if (bytes == 0) chunks.push_back({i, 0, 0, true});      // empty view: only its ready event
@@ -563,7 +564,7 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     return B200M_OK;
   };
   const char* e_lag = getenv("B200M_UP_LAG");
-  const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 2));   // chunks between a memcpy and its H2D
+  const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 4));   // chunks between a memcpy and its H2D (= memcpys in flight)
   std::vector<std::unique_ptr<TaskGroup>> grp(chunks.size());
   auto issue_h2d = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
@@ -582,10 +583,14 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     CK(cudaEventSynchronize(c->stg_ev[sidx]));             // the H2D that last used this staging buffer is done (no-op when never recorded)
     grp[k].reset(new TaskGroup());
     if (ch.bytes) {
-      grp[k]->add(1);
+      // the pageable -> pinned copy of one chunk may be split over pool threads (B200M_UP_PARTS; default 1)
+      const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_parts, ch.bytes >> 19));
+      grp[k]->add(parts);
       char* d = (char*)c->stg[sidx]; const char* sp = (const char*)job.descs[ch.view] + ch.off; TaskGroup* g = grp[k].get();
-      const size_t nb = ch.bytes;
-      c->pool->submit([=] { std::memcpy(d, sp, nb); g->done(); });
+      for (int q = 0; q < parts; ++q) {
+        const size_t a0 = ch.bytes * q / parts, a1 = ch.bytes * (q + 1) / parts;
+        c->pool->submit([=] { std::memcpy(d + a0, sp + a0, a1 - a0); g->done(); });
+      }
     }
     if (k >= (size_t)LAG) { int rc = issue_h2d(k - LAG); if (rc) return rc; }
   }
@@ -1081,6 +1086,141 @@ int b200m_last_launches(const b200m_ctx* c) { return c ? c->last_launches : 0; }
 int b200m_last_tc_pairs(const b200m_ctx* c) { return c ? c->last_tc_pairs : 0; }
 unsigned b200m_exactness_errors(const b200m_ctx* c) { return c ? c->err_total : 0; }
 int64_t b200m_last_records(const b200m_ctx* c) { return c ? c->last_records : 0; }
+
+// ---- Surface 2 on several GPUs from ONE process ----------------------------------------------------------------------
+// The reference binary is a single process (main_featureMatching.cpp): to use every GPU of the node behind the same
+// IImageCollectionMatcher::Match call, the pair list is dealt by database image over one engine context per device
+// (independent units, no exchange step, no collective), each driven by its own host thread; only the views
+// a shard references are uploaded to its GPU, and the per-device results are merged back in PairSet order.
+int b200m_shard_pairs(const uint32_t* pairs, int n_pairs, int n_shards, int32_t* shard_of) {
+  if (n_pairs < 0 || n_shards < 1 || (n_pairs > 0 && (!pairs || !shard_of))) return fail(B200M_ERR_ARG, "bad arguments");
+  // database images (first index, as ImageCollectionMatcher_generic groups them, .cpp:45-50) in ascending order, dealt round-robin,
+  // direction alternating every round so the triangular row lengths of an exhaustive list balance
+  std::set<uint32_t> firsts;
+  for (int k = 0; k < n_pairs; ++k) firsts.insert(pairs[2 * k]);
+  std::unordered_map<uint32_t, int> owner;
+  int k = 0;
+  for (uint32_t f : firsts) {
+    const int rnd = k / n_shards, pos = k % n_shards;
+    owner[f] = (rnd % 2 == 0) ? pos : n_shards - 1 - pos;
+    ++k;
+  }
+  for (int p = 0; p < n_pairs; ++p) shard_of[p] = owner[pairs[2 * p]];
+  return B200M_OK;
+}
+
+struct b200m_multi {
+  std::vector<b200m_ctx*> ctx;
+  double last_gpu_ms_max = 0;
+};
+
+int b200m_multi_create(const int* devices, int n_devices, b200m_multi** out) {
+  if (!out || n_devices < 1 || !devices) return fail(B200M_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  std::unique_ptr<b200m_multi> m(new b200m_multi());
+  for (int d = 0; d < n_devices; ++d) {
+    b200m_ctx* c = nullptr;
+    const int rc = b200m_ctx_create(devices[d], nullptr, &c);
+    if (rc) { for (auto* x : m->ctx) b200m_ctx_destroy(x); return rc; }
+    m->ctx.push_back(c);
+  }
+  // the finishing pools share the host: split the threads
+  const int ht = std::max(2, (int)std::thread::hardware_concurrency() / n_devices);
+  for (auto* c : m->ctx) b200m_ctx_set_host_threads(c, std::min(ht, 32));
+  *out = m.release();
+  return B200M_OK;
+}
+
+void b200m_multi_destroy(b200m_multi* m) {
+  if (!m) return;
+  for (auto* c : m->ctx) b200m_ctx_destroy(c);
+  delete m;
+}
+
+int b200m_multi_num_devices(const b200m_multi* m) { return m ? (int)m->ctx.size() : 0; }
+b200m_ctx* b200m_multi_ctx(b200m_multi* m, int k) { return (m && k >= 0 && k < (int)m->ctx.size()) ? m->ctx[k] : nullptr; }
+double b200m_multi_last_gpu_ms(const b200m_multi* m) { return m ? m->last_gpu_ms_max : 0; }
+
+int b200m_multi_match(b200m_multi* m, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                      const float* const* xys, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, b200m_result** out) {
+  if (!m || !out || n_views < 0 || n_pairs < 0 || (n_views > 0 && (!view_ids || !descs || !counts)) || (n_pairs > 0 && !pairs))
+    return fail(B200M_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  const int nd = (int)m->ctx.size();
+  std::unordered_map<uint32_t, int> index_of;
+  for (int v = 0; v < n_views; ++v) index_of[view_ids[v]] = v;
+  for (int p = 0; p < 2 * n_pairs; ++p)
+    if (!index_of.count(pairs[p]))
+      return fail(B200M_ERR_ARG, "pair references a view that was not given (RegionsPerView::getRegions would throw std::out_of_range)");
+  std::vector<int32_t> shard_of(std::max(n_pairs, 1));
+  int rc = b200m_shard_pairs(pairs, n_pairs, nd, shard_of.data());
+  if (rc) return rc;
+  struct Shard { std::vector<uint32_t> pairs; b200m_result* res = nullptr; int rc = B200M_OK; std::string err; };
+  std::vector<Shard> sh(nd);
+  for (int p = 0; p < n_pairs; ++p) { sh[shard_of[p]].pairs.push_back(pairs[2 * p]); sh[shard_of[p]].pairs.push_back(pairs[2 * p + 1]); }
+  auto run = [&](int d) {
+    Shard& s = sh[d];
+    b200m_ctx* c = m->ctx[d];
+    std::vector<uint32_t> ids; std::vector<const void*> dp; std::vector<int> cnt; std::vector<const float*> xp;
+    {
+      std::set<uint32_t> used(s.pairs.begin(), s.pairs.end());
+      for (uint32_t id : used) { const int v = index_of[id]; ids.push_back(id); dp.push_back(descs[v]); cnt.push_back(counts[v]); xp.push_back(xys ? xys[v] : nullptr); }
+    }
+    s.rc = b200m_clear_views(c);
+    if (!s.rc) s.rc = b200m_upload_views_async(c, (int)ids.size(), ids.data(), dp.data(), cnt.data(), dim, dtype, xys ? xp.data() : nullptr);
+    if (!s.rc) s.rc = b200m_match_pairs(c, s.pairs.data(), (int)(s.pairs.size() / 2), dist_ratio, cross, B200M_STAGE_FULL, &s.res);
+    if (s.rc) s.err = g_err;       // thread-local message of this worker
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < nd; ++d) th.emplace_back(run, d);
+  run(0);
+  for (auto& t : th) t.join();
+  m->last_gpu_ms_max = 0;
+  for (int d = 0; d < nd; ++d) {
+    m->last_gpu_ms_max = std::max(m->last_gpu_ms_max, m->ctx[d]->last_gpu_ms);
+    if (sh[d].rc) {
+      const int code = sh[d].rc; const std::string msg = sh[d].err;
+      for (auto& s : sh) if (s.res) b200m_result_free(s.res);
+      return fail(code, "device " + std::to_string(m->ctx[d]->device) + ": " + msg);
+    }
+  }
+  // merge in PairSet (lexicographic) order: every shard's result is already sorted, and a pair lives in exactly one shard
+  struct Ref { uint32_t i, j; int shard; int64_t k; };
+  std::vector<Ref> order;
+  for (int d = 0; d < nd; ++d) {
+    const b200m_result* r = sh[d].res;
+    for (size_t k = 0; k + 1 < r->offsets.size(); ++k) order.push_back(Ref{r->pair_ids[2 * k], r->pair_ids[2 * k + 1], d, (int64_t)k});
+  }
+  std::sort(order.begin(), order.end(), [](const Ref& a, const Ref& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
+  std::unique_ptr<b200m_result> res(new b200m_result());
+  res->offsets.assign(order.size() + 1, 0);
+  res->pair_ids.reserve(2 * order.size());
+  for (size_t k = 0; k < order.size(); ++k) {
+    const b200m_result* r = sh[order[k].shard].res;
+    res->pair_ids.push_back(order[k].i); res->pair_ids.push_back(order[k].j);
+    res->offsets[k + 1] = res->offsets[k] + (r->offsets[order[k].k + 1] - r->offsets[order[k].k]);
+  }
+  const size_t total = (size_t)res->offsets[order.size()];
+  res->matches.cap = std::max<size_t>(total, 1);
+  res->matches.p = static_cast<b200m_match*>(::operator new(res->matches.cap * sizeof(b200m_match)));
+  {
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto copy = [&](int t) {
+      for (size_t k = (size_t)t; k < order.size(); k += (size_t)nt) {
+        const b200m_result* r = sh[order[k].shard].res;
+        const int64_t a = r->offsets[order[k].k], b = r->offsets[order[k].k + 1];
+        if (b > a) std::memcpy(res->matches.p + res->offsets[k], r->matches.p + a, sizeof(b200m_match) * (size_t)(b - a));
+      }
+    };
+    std::vector<std::thread> ct;
+    for (int t = 1; t < nt; ++t) ct.emplace_back(copy, t);
+    copy(0);
+    for (auto& t : ct) t.join();
+  }
+  for (auto& s : sh) b200m_result_free(s.res);
+  *out = res.release();
+  return B200M_OK;
+}
 
 // ---- Surface 1: ArrayMatcher ------------------------------------------------------------------------------------
 int b200m_db_create(b200m_ctx* c, const void* data, int rows, int dim, int dtype, int metric, b200m_db** out) {

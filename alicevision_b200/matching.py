@@ -35,6 +35,8 @@ ABI_SYMBOLS = [
     "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
+    "b200m_shard_pairs", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
+    "b200m_multi_last_gpu_ms",
 ]
 
 
@@ -69,7 +71,9 @@ def load_library() -> C.CDLL:
     lib.b200m_last_search_kernel_ms.restype = C.c_double
     lib.b200m_last_records.restype = C.c_int64
     lib.b200m_exactness_errors.restype = C.c_uint
-    for name in ("b200m_ctx_destroy", "b200m_db_destroy", "b200m_result_free"):
+    lib.b200m_multi_last_gpu_ms.restype = C.c_double
+    lib.b200m_multi_ctx.restype = C.c_void_p
+    for name in ("b200m_ctx_destroy", "b200m_db_destroy", "b200m_result_free", "b200m_multi_destroy"):
         getattr(lib, name).restype = None
     _lib = lib
     return lib
@@ -236,15 +240,53 @@ class ArrayMatcherB200:
             pass
 
 
+def shard_pairs(pairs, n_shards: int) -> np.ndarray:
+    """b200m_shard_pairs: shard index of every pair (database images dealt round-robin, alternating direction). Host only."""
+    p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    out = np.zeros(max(p.shape[0], 1), np.int32)
+    _check(load_library().b200m_shard_pairs(p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_int(n_shards), out.ctypes.data_as(C.c_void_p)),
+           "b200m_shard_pairs")
+    return out[: p.shape[0]]
+
+
+class MultiContext:
+    """``b200m_multi``: one engine context per device, driven by one host thread each (single-process multi-GPU)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.devices = [int(d) for d in devices]
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(self.lib.b200m_multi_create(arr, C.c_int(len(self.devices)), C.byref(self._h)), "b200m_multi_create")
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.b200m_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_gpu_ms(self) -> float: return self.lib.b200m_multi_last_gpu_ms(self._h)
+
+    def exactness_errors(self) -> int:
+        return sum(self.lib.b200m_exactness_errors(C.c_void_p(self.lib.b200m_multi_ctx(self._h, C.c_int(k)))) for k in range(len(self.devices)))
+
+
 class ImageCollectionMatcherB200:
-    """Mirror of IImageCollectionMatcher / ImageCollectionMatcher_generic (distRatio, crossMatching, matcherType)."""
+    """Mirror of IImageCollectionMatcher / ImageCollectionMatcher_generic (distRatio, crossMatching, matcherType).
+    ``devices``: several CUDA ordinals -> the pair list is sharded over one context per device inside this process."""
 
     def __init__(self, distRatio: float = 0.8, crossMatching: bool = False, matcherType: EMatcherType = EMatcherType.BRUTE_FORCE_L2_B200,
-                 ctx: Context | None = None):
+                 ctx: Context | None = None, devices=None):
         if matcherType not in (EMatcherType.BRUTE_FORCE_L2_B200, EMatcherType.BRUTE_FORCE_HAMMING_B200, EMatcherType.BRUTE_FORCE_L2,
                                EMatcherType.BRUTE_FORCE_HAMMING):
             raise IndexError("Invalid matcherType enum")    # matchingCommon.cpp:41-42 throws std::out_of_range
-        self.ctx = ctx or default_context()
+        self.multi = MultiContext(devices) if devices is not None and len(devices) > 1 else None
+        self.ctx = ctx or (default_context(devices[0] if devices else 0) if self.multi is None else None)
         self.distRatio, self.crossMatching, self.matcherType = float(distRatio), bool(crossMatching), matcherType
         self.hamming = matcherType in (EMatcherType.BRUTE_FORCE_HAMMING_B200, EMatcherType.BRUTE_FORCE_HAMMING)
         self._keepalive = []      # descriptor arrays of asynchronous uploads still in flight
@@ -294,6 +336,9 @@ class ImageCollectionMatcherB200:
                                          C.c_int(int(self.crossMatching)), C.c_int(stage), C.byref(res)), "b200m_match_pairs")
         finally:
             self._keepalive.clear()      # b200m_match_pairs returns after every pending upload has left caller memory
+        return self._wrap_result(lib, res)
+
+    def _wrap_result(self, lib, res):
         owner = _ResultOwner(lib, res)      # the numpy arrays below alias the result's memory; it is freed when they die
         n = lib.b200m_result_num_pairs(res)
         pid, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -303,12 +348,38 @@ class ImageCollectionMatcherB200:
         matches = _alias(mat.value, int(offsets[-1]) * MATCH_DTYPE.itemsize, MATCH_DTYPE, owner)
         return pair_ids, offsets, matches
 
+    def _match_multi(self, regionsPerView: dict, pairs):
+        """b200m_multi_match: all views of ONE element type, pair list sharded over the devices."""
+        lib = self.multi.lib
+        items = []
+        for vid, (desc, xy) in regionsPerView.items():
+            d = np.ascontiguousarray(desc)
+            items.append((vid, d, None if xy is None else np.ascontiguousarray(xy, np.float32)))
+        codes = {(_dtype_code(d, d.dtype == np.uint8 and self.hamming), d.shape[1] if d.ndim == 2 else 0) for _, d, _ in items}
+        if len(codes) != 1:
+            raise B200MatchError("the multi-device path takes views of one descriptor type per call")
+        (code, dim), = codes
+        n = len(items)
+        ids = np.array([v for v, _, _ in items], np.uint32)
+        counts = np.array([d.shape[0] for _, d, _ in items], np.int32)
+        dptr = (C.c_void_p * n)(*[d.ctypes.data if d.shape[0] else None for _, d, _ in items])
+        xptr = (C.c_void_p * n)(*[(x.ctypes.data if x is not None and x.size else None) for _, _, x in items])
+        p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        res = C.c_void_p()
+        _check(lib.b200m_multi_match(self.multi._h, C.c_int(n), ids.ctypes.data_as(C.c_void_p), dptr, counts.ctypes.data_as(C.c_void_p), C.c_int(max(dim, 1)),
+                                     C.c_int(code), xptr, p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_float(self.distRatio),
+                                     C.c_int(int(self.crossMatching)), C.byref(res)), "b200m_multi_match")
+        return self._wrap_result(lib, res)
+
     def Match(self, regionsPerView: dict, pairs, map_PutativesMatches: dict | None = None) -> dict:
         """IImageCollectionMatcher::Match: appends {(I, J): matches} for every pair with a non-empty result
         (ImageCollectionMatcher_generic.cpp:116-119: empty lists are not inserted; the output map is appended to)."""
         out = {} if map_PutativesMatches is None else map_PutativesMatches
-        self.upload(regionsPerView)
-        pair_ids, offsets, matches = self.match_uploaded(pairs, STAGE_FULL)
+        if self.multi is not None:
+            pair_ids, offsets, matches = self._match_multi(regionsPerView, pairs)
+        else:
+            self.upload(regionsPerView)
+            pair_ids, offsets, matches = self.match_uploaded(pairs, STAGE_FULL)
         offs = offsets.tolist()
         for (i, j), a, b in zip(pair_ids.tolist(), offs[:-1], offs[1:]):
             if b > a:

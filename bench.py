@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "u8", "bin"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--tc-variant", type=int, default=4, choices=[1, 2, 3, 4], help="4 = CTA-pair tcgen05 kernel, half-norms folded into the GEMM (default); 2/3 = CTA pair with epilogue add (8/16 epilogue warps); 1 = single-CTA kernel")
+    ap.add_argument("--pairs", default="exhaustive", choices=["exhaustive", "voctree"],
+                    help="voctree = BASELINE configs[2]: synthetic vocabulary-tree style list, 50 neighbours per image (use with --images 1000)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -59,22 +61,18 @@ def make_workload(args, world):
         descs, xys = synth.mldb_images(n_img, args.features, seed=synth.SEED_DATA)
     else:
         descs, xys = synth.sift_images(n_img, args.features, np.float32 if args.dtype == "f32" else np.uint8, seed=synth.SEED_DATA, pool_factor=1.0)
-    pairs = synth.exhaustive_pairs(n_img)
+    pairs = synth.voctree_like_pairs(n_img, k=50) if args.pairs == "voctree" else synth.exhaustive_pairs(n_img)
     return descs, xys, pairs
 
 
 def shard_pairs(pairs: np.ndarray, rank: int, world: int) -> np.ndarray:
-    """Deal database images (first index, as ImageCollectionMatcher_generic groups them, .cpp:45-50) round-robin
-    over ranks, alternating direction every round so the triangular row lengths balance."""
+    """This rank's shard: database images (first index, as ImageCollectionMatcher_generic groups them, .cpp:45-50) dealt
+    round-robin over ranks, direction alternating every round so the triangular row lengths balance.  Same host function
+    (b200m_shard_pairs) the single-process multi-GPU path uses."""
     if world == 1:
         return pairs
-    firsts = np.unique(pairs[:, 0])
-    owner = {}
-    for k, f in enumerate(firsts):
-        rnd, pos = divmod(k, world)
-        owner[int(f)] = pos if rnd % 2 == 0 else world - 1 - pos
-    keep = np.array([owner[int(f)] == rank for f in pairs[:, 0]])
-    return pairs[keep]
+    from alicevision_b200 import matching
+    return pairs[matching.shard_pairs(pairs, world) == rank]
 
 
 class ClockSampler:
@@ -150,6 +148,15 @@ def cpu_baseline(descs, xys, pairs, hamming, budget_s):
     return {"value": n / dt, "unit": "pairs/s", "cores": ora.num_threads(), "kind": "reference" if ora.kind == "ref" else "port",
             "sample": f"first {n} pairs of the same list, {dt:.1f} s, ArrayMatcher_bruteForce + ratio test + de-duplication, "
                       f"{'g++ -O3 -msse2 -fopenmp on the reference headers' if ora.kind == 'ref' else 'C++ port of the reference'}"}
+
+
+def ncu_traffic(kernel_key: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -255,22 +262,28 @@ def main():
             "metric": metric, "value": n_pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32-popcount" if hamming else "f16 (fp16 operands, fp32 accumulate; exact on integer-valued SIFT)", "data": "synthetic",
-            "config": {"workload": f"{len(descs)} synthetic images x {M} {'MLDB 64-byte' if hamming else 'SIFT 128-D ' + args.dtype} features, exhaustive "
+            "config": {"workload": f"{len(descs)} synthetic images x {M} {'MLDB 64-byte' if hamming else 'SIFT 128-D ' + args.dtype} features, "
+                                   f"{'vocabulary-tree style (50 neighbours/image)' if args.pairs == 'voctree' else 'exhaustive'} "
                                    f"{int(n_pairs)} ordered pairs, BRUTE_FORCE_{'HAMMING' if hamming else 'L2'}, ratio 0.8",
                        "pairs_per_gpu": n_pairs / world, "sharding": "pairs dealt round-robin by database image, no collective on the data path",
                        "l2_policy": f"inputs larger than L2 ({len(descs) * M * (64 if hamming else 256) / 1e6:.0f} MB of resident descriptors vs 126 MB L2)",
                        "tensor_core_pairs": tc_pairs, "exactness_errors": errs, "wall_ms_per_step": ms_wall, "records_per_step": records / args.steps},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": (n_pairs / (ms_e2e * 1e-3)) if ms_e2e > 0 else None, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "b200m_upload_view for every view + b200m_match_pairs(STAGE_FULL): H2D, kernels, D2H, host de-duplication"},
+                    "what": "b200m_clear_views + b200m_upload_views_async (every view, from host memory) + b200m_match_pairs(STAGE_FULL): H2D overlapped with the "
+                            "first pairs, kernels, D2H, host de-duplication, {(I,J): matches} map; wall clock"},
         }
         if hamming:
             hb = (n_pairs / world) * 2.0 * M * 64 / (ms_search * 1e-3) / 1e9
             hp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-            out["roofline"] = {"bound": "hbm", "achieved": hb, "peak": hp, "unit": "GB/s", "frac": hb / hp, "traffic": None,
+            tr = ncu_traffic("hamming_top2_kernel")
+            out["roofline"] = {"bound": "hbm", "achieved": hb, "peak": hp, "unit": "GB/s", "frac": hb / hp, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                               "traffic_note": tr["note"] if tr else None,
                                "note": "popc-issue bound by construction (M^2*16 popc32 per pair vs 2*M*64 bytes); HBM fraction reported because the north star asks"}
         else:
-            out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            tr = ncu_traffic("l2_top2_tc2_kernel") if (args.tc_variant == 4 and M == 8192) else None
+            out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                               "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_note": tr["note"] if tr else None,
                                "kernel": {1: "tc::l2_top2_tc_kernel", 2: "tc2::l2_top2_tc2_kernel<8,false> (cta_group::2)", 3: "tc2::l2_top2_tc2_kernel<16,false> (cta_group::2)", 4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant], "peak_source": peak_src, "flop_per_pair": flop_pair,
                                "kernel_ms_per_step": ms_search}
         if not args.no_cpu:

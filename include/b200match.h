@@ -109,6 +109,26 @@ int b200m_result_num_pairs(const b200m_result* r);
 int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int64_t** offsets, const b200m_match** matches);
 void b200m_result_free(b200m_result* r);
 
+/* ---- Surface 2 on several GPUs from one process --------------------------------------------------------------------- */
+/* Which shard (0..n_shards-1) each pair goes to: database images (first id) in ascending order are dealt round-robin over
+ * the shards, direction alternating every round; all pairs of one database image stay together (its descriptors are
+ * reused out of L2, ImageCollectionMatcher_generic.cpp:45-50 groups the same way).  Host-only, no GPU needed. */
+int b200m_shard_pairs(const uint32_t* pairs, int n_pairs, int n_shards, int32_t* shard_of);
+
+typedef struct b200m_multi b200m_multi;   /* one engine context per device + one host thread each */
+int b200m_multi_create(const int* devices, int n_devices, b200m_multi** out);
+void b200m_multi_destroy(b200m_multi* m);
+int b200m_multi_num_devices(const b200m_multi* m);
+b200m_ctx* b200m_multi_ctx(b200m_multi* m, int k);
+/* One IImageCollectionMatcher::Match call on all devices: shards the pair list (b200m_shard_pairs), uploads to each GPU
+ * only the views its shard references (asynchronously, overlapped with its first pairs), runs b200m_match_pairs
+ * (B200M_STAGE_FULL) per device on its own host thread and merges the results in PairSet order.  No data-path
+ * collective: pairs are independent.  Views are given as in b200m_upload_views; previous views of the contexts are dropped. */
+int b200m_multi_match(b200m_multi* m, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
+                      const float* const* xys, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, b200m_result** out);
+/* max over devices of the GPU time of the last b200m_multi_match, ms */
+double b200m_multi_last_gpu_ms(const b200m_multi* m);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
 /* GPU time of the last b200m_match_pairs between its first and last enqueue (CUDA events on the context's stream), ms */
 double b200m_last_gpu_ms(const b200m_ctx* ctx);

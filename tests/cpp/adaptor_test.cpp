@@ -152,6 +152,22 @@ int main()
                 CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j && w[k]._distanceRatio == g[k]._distanceRatio && w[k]._distance == g[k]._distance);
         }
         std::printf("collection cross=%d: %zu pairs compared\n", cross, want.size());
+        // the same call sharded over two engine contexts inside this process (b200m_multi_match; both on device 0 here)
+        matchingImageCollection::ImageCollectionMatcher_b200 multi(0.8f, cross != 0, false, std::vector<int>{0, 0});
+        PairwiseMatches got2;
+        multi.Match(rng, rpv, pairs, EImageDescriberType::SIFT, got2);
+        CHECK(got2.size() == got.size());
+        for (auto& kv : got)
+        {
+            auto it = got2.find(kv.first);
+            CHECK(it != got2.end());
+            if (it == got2.end()) continue;
+            const IndMatches& w = kv.second.at(EImageDescriberType::SIFT);
+            const IndMatches& g = it->second.at(EImageDescriberType::SIFT);
+            CHECK(w.size() == g.size());
+            for (size_t k = 0; k < std::min(w.size(), g.size()); ++k)
+                CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j && w[k]._distanceRatio == g[k]._distanceRatio && w[k]._distance == g[k]._distance);
+        }
     }
     // --- IRegionsMatcher adaptor (what createRegionsMatcher returns for the new enum values) vs the reference's
     //     RegionsMatcher<ArrayMatcher_bruteForce<...>>: one database, several queries, uchar / float / binary, factory rules

@@ -298,3 +298,81 @@ def test_async_upload_overlaps_and_keeps_pairset_order(ora, cross):
     pid2, off2, mat2 = m.match_uploaded(pairs)
     assert np.array_equal(pid, pid2) and np.array_equal(off, off2) and np.array_equal(mat, mat2)
     m.clear()
+
+
+# ---------------------------------------------------------------------------------------------- single-process multi-device
+@pytest.mark.parametrize("cross", [False, True])
+def test_multi_device_single_process(ora, cross):
+    """b200m_multi_match: the pair list sharded over several engine contexts inside one process, merged in PairSet order.
+    Uses every visible GPU, and at least two contexts (both on device 0 when the box has one GPU)."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    n = 9
+    descs, xys = synth.sift_images(n, 700, np.uint8, seed=55, pool_factor=1.0)
+    descs[3] = descs[3][:0]; xys[3] = xys[3][:0]
+    pairs = np.concatenate([synth.exhaustive_pairs(n), [[7, 2], [8, 0]]])        # includes I > J pairs, kept as given (PairSet semantics)
+    m = ImageCollectionMatcherB200(0.8, cross, EMatcherType.BRUTE_FORCE_L2_B200, devices=devices)
+    got = m.Match({i: (descs[i], xys[i]) for i in range(n)}, pairs)
+    want = ora.collection_match(descs, xys, pairs, 0.8, cross=cross)
+    assert_same(got, want)
+    assert list(got) == sorted(got)                    # merged in PairSet order
+    assert m.multi.exactness_errors() == 0
+    got2 = m.Match({i: (descs[i], xys[i]) for i in range(n)}, pairs)      # contexts are reused by the next call
+    assert_same(got2, want)
+    m.multi.close()
+
+
+# ---------------------------------------------------------------------------------------------- more full-size properties
+def test_full_size_cross_matching_is_symmetric():
+    """BASELINE config size (8192): with cross matching the kept correspondences of (I, J) are the transposed kept
+    correspondences of (J, I) (a match survives iff it is a ratio-test match in both directions,
+    ImageCollectionMatcher_generic.cpp:83-111) - as long as no coordinate de-duplication removes one side, which the
+    generic synthetic positions guarantee only for the left image, so the property is checked on the (i, j) SETS of
+    the raw mutual matches: cross(I,J) subset of fwd(I,J), and {(i,j)} == {(j,i) of cross(J,I)} for features matched once."""
+    m = 8192
+    descs, xys = synth.sift_images(2, m, np.uint8, seed=92, pool_factor=1.0)
+    fwd, _ = run(descs, xys, [(0, 1), (1, 0)], cross=False)
+    crs, mm = run(descs, xys, [(0, 1), (1, 0)], cross=True)
+    assert mm.ctx.exactness_errors() == 0
+    f01 = set(zip(fwd[(0, 1)]["i"].tolist(), fwd[(0, 1)]["j"].tolist())); f10 = set(zip(fwd[(1, 0)]["i"].tolist(), fwd[(1, 0)]["j"].tolist()))
+    c01 = set(zip(crs[(0, 1)]["i"].tolist(), crs[(0, 1)]["j"].tolist())); c10 = set(zip(crs[(1, 0)]["i"].tolist(), crs[(1, 0)]["j"].tolist()))
+    assert c01 <= f01 and c10 <= f10 and len(c01) > 0.03 * m
+    assert c01 == {(i, j) for (i, j) in f01 if (j, i) in f10}
+    assert c10 == {(i, j) for (i, j) in f10 if (j, i) in f01}
+    assert c01 == {(j, i) for (i, j) in c10}
+
+
+def test_full_size_hamming_properties():
+    """BASELINE configs[3] size (16384 MLDB features): self-match identity, planted correspondences, and a numpy popcount
+    check of the two smallest distances for a sample of queries."""
+    m = 16384
+    descs, xys = synth.mldb_images(2, m, seed=93)
+    got, _ = run(descs, xys, [(0, 0), (0, 1)], hamming=True)
+    s = got[(0, 0)]
+    assert np.array_equal(s["i"], s["j"]) and np.all(s["dist"] == 0) and len(s) > 0.9 * m and np.all(s["ratio"] == 0)
+    g = got[(0, 1)]
+    assert len(g) > 0.05 * m
+    rng = np.random.default_rng(3)
+    pick = rng.choice(len(g), 48, replace=False)
+    lut = np.array([bin(v).count("1") for v in range(256)], np.uint16)
+    for k in pick:
+        i, j = int(g["i"][k]), int(g["j"][k])
+        d = lut[np.bitwise_xor(descs[0], descs[1][j][None, :])].sum(axis=1)
+        o = np.argsort(d, kind="stable")
+        assert o[0] == i and d[o[0]] == g["dist"][k] and np.float32(d[o[0]]) < np.float32(0.8) * np.float32(d[o[1]])
+    # queries the kernel rejected really fail the ratio test
+    rejected = np.setdiff1d(np.arange(m), g["j"])[:24]
+    for j in rejected:
+        d = np.sort(lut[np.bitwise_xor(descs[0], descs[1][j][None, :])].sum(axis=1))
+        assert not (np.float32(d[0]) < np.float32(0.8) * np.float32(d[1]))
+
+
+def test_largest_sweep_size_32k():
+    """BASELINE configs[4] upper end (32768 features/image): tensor-core result == exact CUDA-core result bit for bit."""
+    m = 32768
+    descs, xys = synth.sift_images(2, m, np.uint8, seed=94, pool_factor=1.0)
+    got, mm = run(descs, xys, [(0, 1)])
+    assert mm.ctx.exactness_errors() == 0 and mm.ctx.last_tc_pairs() == 1 and len(got[(0, 1)]) > 0.03 * m
+    got_exact, _ = run(descs, xys, [(0, 1)], force_exact=True)
+    assert_same(got_exact, got)

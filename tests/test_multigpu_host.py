@@ -61,3 +61,25 @@ def test_shard_sizes_weak_scaling_table():
         assert sum(sizes) == len(pairs)
         assert max(sizes) - min(sizes) <= n_img
         assert abs(np.mean(sizes) - 4950) / 4950 < 0.02
+
+
+def test_c_sharding_properties():
+    """b200m_shard_pairs (host function of the C ABI, used by bench.py under torchrun and by b200m_multi_match in-process):
+    disjoint cover, all pairs of one database image on one shard, balanced for exhaustive and for sparse lists."""
+    sys.path.insert(0, ROOT)
+    from alicevision_b200 import matching, synth
+    for n_img, world in ((23, 2), (100, 4), (282, 8), (7, 8)):
+        pairs = synth.exhaustive_pairs(n_img)
+        s = matching.shard_pairs(pairs, world)
+        assert s.min() >= 0 and s.max() < world and len(s) == len(pairs)
+        owner = {}
+        for (i, _), k in zip(pairs.tolist(), s.tolist()):
+            assert owner.setdefault(i, k) == k
+        sizes = np.bincount(s, minlength=world)
+        if n_img > 2 * world:
+            assert sizes.max() - sizes.min() <= n_img
+    vt = synth.voctree_like_pairs(300, k=20)
+    s = matching.shard_pairs(vt, 8)
+    sizes = np.bincount(s, minlength=8)
+    assert sizes.sum() == len(vt) and sizes.max() < 1.35 * sizes.mean()
+    assert len(matching.shard_pairs(np.zeros((0, 2), np.uint32), 4)) == 0
