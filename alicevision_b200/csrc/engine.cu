@@ -188,6 +188,9 @@ struct b200m_ctx {
   std::deque<UploadJob> up_jobs; bool up_quit = false; int up_active = 0;
   uint64_t up_issued_seq = 0, next_seq = 0;   // last view whose ready event was recorded / last sequence number handed out
   int up_rc = 0; std::string up_err;
+  // the entry points that touch views, batch buffers or the stream serialise on this lock: one context may be shared by
+  // several host threads (e.g. IRegionsMatcher adaptors created from an OpenMP region); calls simply queue up
+  std::recursive_mutex api_mu;
   unsigned int* d_err = nullptr;
   long long* d_trace = nullptr;   // optional pipeline trace of CTA 0 (debug)
   int dbg_ablate = 0;             // debug-only ablation switch of the CTA-pair kernel (results are WRONG when non-zero)
@@ -517,8 +520,8 @@ int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
 
 // ---- Surface 2: views -------------------------------------------------------------------------------------------
 // Uploads run on their own thread and their own stream (`up_stream`): caller memory is pageable, so descriptors go through
-// a ring of pinned staging buffers (pool threads memcpy chunk k+1 / k+2 into pinned memory while the copy engine moves
-// chunk k; the H2D of a chunk is issued two chunks behind its memcpy) and each view's preparation kernel, the copy of its
+// a ring of pinned staging buffers (pool threads memcpy chunks k+1..k+4 into pinned memory while the copy engine moves
+// chunk k; the H2D of a chunk is issued four chunks behind its memcpy) and each view's preparation kernel, the copy of its
 // exactness flags to pinned host memory and its "ready" event follow its last chunk.  b200m_match_pairs only waits for the
 // views of the batch it is about to enqueue, so the search kernels of the first pairs run while later views are still
 // being copied (the pair list is processed in order of view arrival when uploads are in flight).
@@ -652,6 +655,7 @@ int b200m_wait_uploads(b200m_ctx* c) {
 int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
                              const float* const* xys) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   if (n_views < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n_views > 0 && (!view_ids || !descs || !counts))) return fail(B200M_ERR_ARG, "bad view arguments");
   for (int i = 0; i < n_views; ++i) if (counts[i] < 0 || (counts[i] > 0 && !descs[i])) return fail(B200M_ERR_ARG, "bad view arguments");
   CK(cudaSetDevice(c->device));
@@ -715,6 +719,8 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
 
 int b200m_upload_views(b200m_ctx* c, int n_views, const uint32_t* view_ids, const void* const* descs, const int* counts, int dim, int dtype,
                        const float* const* xys) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   int rc = b200m_upload_views_async(c, n_views, view_ids, descs, counts, dim, dtype, xys);
   if (rc) return rc;
   return wait_uploads(c);
@@ -727,6 +733,7 @@ int b200m_upload_view(b200m_ctx* c, uint32_t view_id, const void* desc, int n, i
 
 int b200m_clear_views(b200m_ctx* c) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   CK(cudaSetDevice(c->device));
   int rc = wait_uploads(c);
   if (rc) return rc;
@@ -740,6 +747,7 @@ int b200m_clear_views(b200m_ctx* c) {
 
 int b200m_remove_view(b200m_ctx* c, uint32_t view_id) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   auto it = c->slot_of.find(view_id);
   if (it == c->slot_of.end()) return fail(B200M_ERR_ARG, "unknown view id");
   CK(cudaSetDevice(c->device));
@@ -761,6 +769,8 @@ struct Directed { int slot_i, slot_j; uint32_t mode; int fwd_index; bool reverse
 static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out);
 
 int b200m_match_pairs(b200m_ctx* c, const uint32_t* pairs, int n_pairs, float dist_ratio, int cross, int stage, b200m_result** out) {
+  if (!c) return fail(B200M_ERR_ARG, "ctx is null");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   const int rc = match_pairs_impl(c, pairs, n_pairs, dist_ratio, cross, stage, out);
   if (c) {
     // asynchronous uploads read caller memory until their copies are issued: that is guaranteed on return, error or not
@@ -1225,6 +1235,7 @@ int b200m_multi_match(b200m_multi* m, int n_views, const uint32_t* view_ids, con
 // ---- Surface 1: ArrayMatcher ------------------------------------------------------------------------------------
 int b200m_db_create(b200m_ctx* c, const void* data, int rows, int dim, int dtype, int metric, b200m_db** out) {
   if (!c || !out) return fail(B200M_ERR_ARG, "bad arguments");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   *out = nullptr;
   if (rows < 1) return fail(B200M_ERR_EMPTY, "Build: nbRows < 1 (ArrayMatcher_bruteForce.hpp:44-48)");
   if (!data || dim < 1 || dtype < 0 || dtype > 2 || metric < 0 || metric > 2) return fail(B200M_ERR_ARG, "bad database arguments");
@@ -1248,6 +1259,7 @@ void b200m_db_destroy(b200m_db* db) {
 
 int b200m_knn(b200m_ctx* c, const b200m_db* db, const void* query, int nq, int nn, int32_t* idx, void* dist) {
   if (!c || !db) return fail(B200M_ERR_ARG, "matcher not built (ArrayMatcher_bruteForce.hpp:100-103)");
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   if (nn < 1 || nn > db->v.m || nq < 1) return fail(B200M_ERR_ARG, "NN > rows or nbQuery < 1 (ArrayMatcher_bruteForce.hpp:105-108)");
   if (nn > GEN_MAX_NN) return fail(B200M_ERR_UNSUPPORTED, "NN > 16 is not supported");
   if (!query || !idx || !dist) return fail(B200M_ERR_ARG, "null buffers");

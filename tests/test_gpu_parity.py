@@ -376,3 +376,33 @@ def test_largest_sweep_size_32k():
     assert mm.ctx.exactness_errors() == 0 and mm.ctx.last_tc_pairs() == 1 and len(got[(0, 1)]) > 0.03 * m
     got_exact, _ = run(descs, xys, [(0, 1)], force_exact=True)
     assert_same(got_exact, got)
+
+
+def test_shared_context_from_several_host_threads(ora):
+    """One engine context used by several host threads at once (IRegionsMatcher adaptors built inside an OpenMP region share
+    b200detail::sharedContext()): calls serialise on the context's lock and every thread gets the reference's result."""
+    import threading
+    from alicevision_b200 import Regions, RegionsMatcherB200
+    descs, xys = synth.sift_images(5, 600, np.uint8, seed=61, pool_factor=1.0)
+    regs = [Regions(d, x) for d, x in zip(descs, xys)]
+    want = {(a, b): ora.regions_match(descs[a], xys[a], descs[b], xys[b], 0.8, False)[1] for a in range(5) for b in range(5) if a != b}
+    errors = []
+
+    def worker(a):
+        try:
+            db = RegionsMatcherB200(regs[a])
+            for rep in range(2):
+                for b in range(5):
+                    if b != a:
+                        ok, got = db.Match(0.8, regs[b])
+                        assert_same({0: got}, {0: want[(a, b)]})
+            db.close()
+        except Exception as e:      # noqa: BLE001
+            errors.append((a, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(a,)) for a in range(5)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
