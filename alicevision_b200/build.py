@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libb200match.so")
-SOURCES = ["engine.cu", "io.cpp"]
-HEADERS = ["common.cuh", "ptx.cuh", "l2_tc.cuh", "l2_tc2.cuh", "l2_exact.cuh", "hamming.cuh", "prep.cuh", "verify.cuh", "../../include/b200match.h", "../../include/b200io.h"]
+SOURCES = ["engine.cu", "voctree.cu", "io.cpp"]
+HEADERS = ["common.cuh", "ptx.cuh", "l2_tc.cuh", "l2_tc2.cuh", "l2_exact.cuh", "hamming.cuh", "prep.cuh", "verify.cuh", "../../include/b200match.h", "../../include/b200io.h", "../../include/b200voc.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # explicit form: `-arch=sm_100a` also emits compute_100 PTX, which rejects tcgen05

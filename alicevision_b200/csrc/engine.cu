@@ -38,6 +38,7 @@ using namespace b200m;
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+namespace b200m { int set_error(int code, const std::string& msg) { return fail(code, msg); } }   // for the other translation units of the library
 #define CK(call)                                                                                          \
   do {                                                                                                    \
     cudaError_t e_ = (call);                                                                              \

@@ -101,3 +101,36 @@ def voctree_like_pairs(n: int, k: int = 50, seed: int = SEED_PAIRS) -> np.ndarra
             if int(j) != i:
                 s.add((min(i, int(j)), max(i, int(j))))
     return np.array(sorted(s), np.uint32).reshape(-1, 2)
+
+
+def vocabulary_tree(k: int = 8, levels: int = 3, seed: int = 4, pool: np.ndarray | None = None, invalid_tail: int = 0):
+    """A synthetic vocabulary tree in the reference's layout (voctree/VocabularyTree.hpp:139-146): node centers level by level,
+    children of node i at (i+1)*k.., float centers.  Centers are SIFT-like descriptors (from `pool` or freshly drawn) with
+    real-valued jitter, children scattered around their parent so that the descent is meaningful.  `invalid_tail` marks the
+    last children of some nodes invalid (fewer than k children, :182-183)."""
+    rng = np.random.default_rng(seed)
+    n_nodes = sum(k ** (l + 1) for l in range(levels))
+    base = sift_pool(max(k, 64), rng).astype(np.float32) if pool is None else np.asarray(pool, np.float32)
+    centers = np.zeros((n_nodes, 128), np.float32)
+    valid = np.ones(n_nodes, np.uint8)
+    first = 0
+    parents = None
+    for l in range(levels):
+        cnt = k ** (l + 1)
+        if parents is None:
+            c = base[rng.choice(len(base), cnt, replace=len(base) < cnt)] + rng.normal(0, 0.37, (cnt, 128)).astype(np.float32)
+        else:
+            spread = 24.0 / (l + 1)
+            c = np.repeat(parents, k, axis=0) + rng.normal(0, spread, (cnt, 128)).astype(np.float32)
+        centers[first:first + cnt] = np.maximum(c, 0)
+        parents = centers[first:first + cnt]
+        first += cnt
+    if invalid_tail:
+        start = 0
+        for l in range(levels):
+            cnt = k ** (l + 1)
+            groups = cnt // k
+            for g in rng.choice(groups, max(1, groups // 5), replace=False):
+                valid[start + g * k + k - invalid_tail:start + (g + 1) * k] = 0
+            start += cnt
+    return centers, valid

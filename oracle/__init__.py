@@ -229,6 +229,57 @@ class Oracle:
         return [((int(ids[b, 0]), int(ids[b, 1])), bytes(names[b]).split(b"\0")[0].decode(), data[offs[b]:offs[b + 1]].copy()) for b in range(nb)]
 
 
+class VoctreeOracle:
+    """CPU statement of the vocabulary-tree pair-list producer (oracle/voctree_oracle.cpp): kind "ref" = the reference's own
+    VocabularyTree.hpp / VocabularyTree.cpp compiled from /root/reference, kind "port" = the restatement."""
+
+    def __init__(self, kind: str = "port"):
+        assert kind in ("ref", "port")
+        self.kind = kind
+        path = os.path.join(_HERE, "_ref", "libref_voctree.so") if kind == "ref" else os.path.join(_HERE, "libport_voctree.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run oracle.build()")
+        self.lib = C.CDLL(path)
+        self.pfx = "refv_" if kind == "ref" else "portv_"
+        getattr(self.lib, self.pfx + "image_matching").restype = C.c_long
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        return os.path.exists(os.path.join(_HERE, "_ref", "libref_voctree.so") if kind == "ref" else os.path.join(_HERE, "libport_voctree.so"))
+
+    def _tree_args(self, k, levels, centers, valid, tmp):
+        c = np.ascontiguousarray(centers, np.float32); v = np.ascontiguousarray(valid, np.uint8)
+        return [C.c_uint32(k), C.c_uint32(levels), _p(c), _p(v), C.c_uint32(c.shape[0]), tmp.encode()], (c, v)
+
+    def quantize(self, k, levels, centers, valid, descs, tmp_tree_path="/tmp/_oracle.tree") -> np.ndarray:
+        d = np.ascontiguousarray(descs)
+        args, keep = self._tree_args(k, levels, centers, valid, tmp_tree_path)
+        words = np.zeros(d.shape[0], np.int32)
+        r = getattr(self.lib, self.pfx + "quantize")(*args, _p(d), C.c_long(d.shape[0]), C.c_int(0 if d.dtype == np.float32 else 1), _p(words))
+        assert r == 0, r
+        return words
+
+    def image_matching(self, k, levels, centers, valid, descs_per_view: dict, nmax=0, numImageQuery=0, method="strongCommonPoints",
+                       tmp_tree_path="/tmp/_oracle.tree"):
+        """Returns (query_ids, match_ids[n, keep], scores[n, keep], weights[num_words], pairs[m, 2])."""
+        ids = np.array(sorted(descs_per_view), np.uint32)
+        ds = [np.ascontiguousarray(descs_per_view[int(i)], np.uint8) for i in ids]
+        n = len(ids)
+        args, keep_alive = self._tree_args(k, levels, centers, valid, tmp_tree_path)
+        dptr = (C.c_void_p * max(n, 1))(*[d.ctypes.data for d in ds])
+        counts = np.array([d.shape[0] for d in ds], np.int64)
+        keep = n if numImageQuery == 0 else min(numImageQuery, n)
+        mids = np.zeros((n, max(keep, 1)), np.uint32); sc = np.zeros((n, max(keep, 1)), np.float32)
+        num_words = k ** levels
+        w = np.zeros(num_words, np.float32)
+        cap = n * max(keep, 1) + 1
+        pairs = np.zeros((cap, 2), np.uint32); npairs = C.c_long()
+        r = getattr(self.lib, self.pfx + "image_matching")(*args, C.c_int(n), _p(ids), dptr, _p(counts), C.c_long(nmax), C.c_long(numImageQuery), method.encode(),
+                                                           C.c_long(numImageQuery), _p(mids), _p(sc), _p(w), _p(pairs), C.c_long(cap), C.byref(npairs))
+        assert r == keep, (r, keep)
+        return ids, mids[:, :keep], sc[:, :keep], w, pairs[: npairs.value].copy()
+
+
 def best(prefer_ref: bool = True) -> Oracle:
     """The strongest checker available: the compiled reference if its .so exists, else the port."""
     if prefer_ref and available("ref"):

@@ -29,6 +29,11 @@ def test_header_symbols_exported():
     assert len(io_names) >= 12 and sorted(regions_io.IO_SYMBOLS) == io_names
     for n in io_names:
         assert hasattr(lib, n), f"{n} declared in include/b200io.h but not exported"
+    from alicevision_b200 import voctree
+    voc_names = header_functions("b200voc.h", "b200v_")
+    assert len(voc_names) >= 19 and sorted(voctree.VOC_SYMBOLS) == voc_names
+    for n in voc_names:
+        assert hasattr(lib, n), f"{n} declared in include/b200voc.h but not exported"
 
 
 def test_no_gpu_fails_loudly():

@@ -134,3 +134,21 @@ def test_edge_cases(oracles, kind):
     assert o.regions_match(descs[0][:1], xys[0][:1], descs[1], xys[1])[0] is False   # NN=2 > 1 row
     res = o.collection_match([descs[0], e, descs[2][:77]], [xys[0], exy, xys[2][:77]], synth.exhaustive_pairs(3))
     assert set(res) <= {(0, 2)}
+
+
+def test_baseline_config0_cpu_plumbing(oracles):
+    """BASELINE.json configs[0]: 2 synthetic images x 1000 SIFT features, BRUTE_FORCE_L2 on the CPU, no GPU - the
+    reference's own ArrayMatcher_bruteForce -> RegionsMatcher -> collection loop (compiled reference when available) and
+    the port give the same putative matches, planted correspondences are found, and the pair-list plumbing
+    (exhaustivePairs -> savePairs -> loadPairs) feeds it."""
+    from alicevision_b200 import pairs as pairs_io
+    descs, xys = synth.sift_images(2, 1000, np.float32, seed=synth.SEED_DATA, pool_factor=1.0)
+    plist = pairs_io.loadPairs(pairs_io.savePairs(pairs_io.exhaustivePairs([0, 1])))
+    assert plist == [(0, 1)]
+    results = {k: o.collection_match(descs, xys, np.array(plist, np.uint32), 0.8) for k, o in oracles.items()}
+    first = next(iter(results.values()))
+    assert list(first) == [(0, 1)] and len(first[(0, 1)]) > 50
+    for r in results.values():
+        assert r.keys() == first.keys() and np.array_equal(r[(0, 1)], first[(0, 1)])
+    m = first[(0, 1)]
+    assert np.all(m["ratio"] < 0.64 + 1e-6) and np.all(m["i"] < 1000) and np.all(m["j"] < 1000) and len(np.unique(m["i"])) == len(m)
