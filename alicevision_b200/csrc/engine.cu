@@ -178,7 +178,7 @@ struct b200m_ctx {
   ViewDev* d_views = nullptr; uint32_t* d_flags = nullptr; int view_cap = 0;
   BatchBuf buf[2]; bool bufs_ready = false;
   // upload staging: pageable caller memory -> pinned ring (parallel memcpy on the pool) -> async H2D
-  static constexpr int NSTG = 8;
+  static constexpr int NSTG = 24;
   void* stg[NSTG] = {}; size_t stg_bytes[NSTG] = {}; cudaEvent_t stg_ev[NSTG] = {};
   ViewDev* h_views = nullptr;     // pinned mirror of the device view table (source of the async table updates)
   uint32_t* h_flags = nullptr;    // pinned: per-slot exactness flags, copied back behind each view's preparation kernel
@@ -568,7 +568,7 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     return B200M_OK;
   };
   const char* e_lag = getenv("B200M_UP_LAG");
-  const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 4));   // chunks between a memcpy and its H2D (= memcpys in flight)
+  const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 12));   // chunks between a memcpy and its H2D (= memcpys in flight)
   std::vector<std::unique_ptr<TaskGroup>> grp(chunks.size());
   auto issue_h2d = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
@@ -996,22 +996,33 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       // because enqueue(bi+2) overwrites it.
       arena.b[bi] = c->recycler->take((size_t)std::max(total, 1));
       TaskGroup* grp = groups[bi].get();
-      int ntasks = 0;
-      for (int p = 0; p < np; ++p) if (dir[seqv[B.begin + p]].mode != PM_SKIP && bb.h_meta[p] > 0) ++ntasks;
-      grp->add(ntasks);
+      // one pool task per ~4096 records (or 64 pairs): for small images the task hand-off would otherwise cost more than the work
+      struct Job { const Rec* recs; int cnt; b200m_match* dst; int* len; const ViewHost* vi; const ViewHost* vj; bool ham; };
+      auto jobs = std::make_shared<std::vector<Job>>();
+      long job_records = 0;
+      const bool full = stage == B200M_STAGE_FULL;
+      auto flush = [&] {
+        if (jobs->empty()) return;
+        grp->add(1);
+        std::shared_ptr<std::vector<Job>> mine = std::move(jobs);
+        c->pool->submit([mine, grp, full] {
+          for (const Job& j : *mine) *j.len = finish_directed(j.recs, j.cnt, j.ham, full, *j.vi, *j.vj, j.dst);
+          grp->done();
+        });
+        jobs = std::make_shared<std::vector<Job>>();
+        job_records = 0;
+      };
       for (int p = 0; p < np; ++p) {
         const size_t di = seqv[B.begin + p];
         const Directed d = dir[di];
         dir_ptr[di] = arena.b[bi].p + bb.h_meta[PAIR_CAP + p];
         const int cnt = bb.h_meta[p];
         if (d.mode == PM_SKIP || cnt == 0) continue;
-        const Rec* recs = bb.h_out + bb.h_meta[PAIR_CAP + p];
-        b200m_match* dst = dir_ptr[di];
-        int* len = &dir_len[di];
-        const ViewHost* vi = &c->views[d.slot_i]; const ViewHost* vj = &c->views[d.slot_j];
-        const bool ham = d.mode == PM_HAMMING, full = stage == B200M_STAGE_FULL;
-        c->pool->submit([=] { *len = finish_directed(recs, cnt, ham, full, *vi, *vj, dst); grp->done(); });
+        jobs->push_back(Job{bb.h_out + bb.h_meta[PAIR_CAP + p], cnt, dir_ptr[di], &dir_len[di], &c->views[d.slot_i], &c->views[d.slot_j], d.mode == PM_HAMMING});
+        job_records += cnt;
+        if (job_records >= 4096 || jobs->size() >= 64) flush();
       }
+      flush();
     }
     const double t_loop = now();
     for (auto& g : groups) g->wait();

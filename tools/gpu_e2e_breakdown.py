@@ -4,8 +4,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from alicevision_b200 import EMatcherType, ImageCollectionMatcherB200, matching, synth
-n_img = 100
-descs, xys = synth.sift_images(n_img, 8192, np.float32, seed=synth.SEED_DATA, pool_factor=1.0)
+n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+n_feat = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+descs, xys = synth.sift_images(n_img, n_feat, np.float32, seed=synth.SEED_DATA, pool_factor=1.0)
 pairs = synth.exhaustive_pairs(n_img)
 views = {i: (descs[i], xys[i]) for i in range(n_img)}
 m = ImageCollectionMatcherB200(0.8, False, EMatcherType.BRUTE_FORCE_L2_B200)

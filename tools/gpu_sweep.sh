@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 : > gpurun_out/sweep.jsonl
 for spec in "1024 200" "2048 160" "4096 120" "8192 100" "16384 48" "32768 24"; do
   set -- $spec
-  timeout 900 python bench.py --features $1 --images $2 --steps 3 --warmup 3 --cpu-seconds 6 >> gpurun_out/sweep.jsonl 2>gpurun_out/sweep_err.log || echo "{\"failed\": \"$spec\"}" >> gpurun_out/sweep.jsonl
+  timeout 900 python bench.py --features $1 --images $2 --steps 3 --warmup 3 --cpu-seconds 4 >> gpurun_out/sweep.jsonl 2>gpurun_out/sweep_err.log || echo "{\"failed\": \"$spec\"}" >> gpurun_out/sweep.jsonl
 done
 python - <<'PY'
 import json

@@ -10,7 +10,7 @@ pairs = synth.exhaustive_pairs(n_img)
 views = {i: (descs[i], xys[i]) for i in range(n_img)}
 m = ImageCollectionMatcherB200(0.8, False, EMatcherType.BRUTE_FORCE_L2_B200)
 m.Match(views, pairs)
-for parts, chunk, lag in ((1, 4, 2), (1, 4, 3), (1, 4, 4), (1, 8, 2), (1, 8, 4), (1, 16, 2), (1, 2, 4), (1, 1, 4), (1, 4, 1)):
+for parts, chunk, lag in ((1, 4, 4), (1, 4, 8), (1, 4, 12), (1, 4, 16), (1, 4, 22), (1, 2, 16), (1, 2, 22), (1, 8, 8), (2, 4, 8)):
     os.environ["B200M_UP_PARTS"] = str(parts); os.environ["B200M_UP_CHUNK_MB"] = str(chunk); os.environ["B200M_UP_LAG"] = str(lag)
     ts, up = [], []
     for rep in range(4):
