@@ -7,6 +7,7 @@
 #include "../../include/b200match.h"
 
 #include "common.cuh"
+#include "guided.cuh"
 #include "hamming.cuh"
 #include "l2_exact.cuh"
 #include "l2_tc.cuh"
@@ -1108,6 +1109,71 @@ int b200m_last_launches(const b200m_ctx* c) { return c ? c->last_launches : 0; }
 int b200m_last_tc_pairs(const b200m_ctx* c) { return c ? c->last_tc_pairs : 0; }
 unsigned b200m_exactness_errors(const b200m_ctx* c) { return c ? c->err_total : 0; }
 int64_t b200m_last_records(const b200m_ctx* c) { return c ? c->last_records : 0; }
+
+// ---- guided matching (after the path: GeometricFilterMatrix_F_AC.hpp:363-390 -> matching/guidedMatching.hpp:206-268) ----------------
+int b200m_guided_match(b200m_ctx* c, uint32_t view_left, uint32_t view_right, const double* F, double errorTh, double distRatio, b200m_result** out) {
+  if (!c || !out || !F) return fail(B200M_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
+  CK(cudaSetDevice(c->device));
+  auto sl = c->slot_of.find(view_left), sr = c->slot_of.find(view_right);
+  if (sl == c->slot_of.end() || sr == c->slot_of.end()) return fail(B200M_ERR_ARG, "guided matching references a view that was never uploaded");
+  int rc;
+  if ((rc = ensure_view_ready(c, sl->second)) || (rc = ensure_view_ready(c, sr->second))) return rc;
+  if ((rc = wait_uploads(c))) return rc;
+  const ViewHost& vl = c->views[sl->second]; const ViewHost& vr = c->views[sr->second];
+  std::unique_ptr<b200m_result> res(new b200m_result());
+  res->pair_ids = {view_left, view_right};
+  res->offsets = {0, 0};
+  res->recycler = c->recycler;
+  const bool usable = vl.m > 0 && vr.m > 0 && vl.dtype == vr.dtype && vl.dim == vr.dim;      // common descriptor type, :300-306
+  if (usable) {
+    if (!((vl.dtype == DT_BIN && vl.dim == 64) || (vl.dtype != DT_BIN && vl.dim == 128)))
+      return fail(B200M_ERR_UNSUPPORTED, "guided matching takes 128-component scalar or 64-byte binary descriptors");
+    if (vl.xy.empty() || vr.xy.empty()) return fail(B200M_ERR_ARG, "guided matching needs feature positions for both views");
+    float* d_xy = nullptr; double2* d_xl = nullptr; double2* d_xr = nullptr; Rec* d_out = nullptr; int* d_cnt = nullptr;
+    cudaStream_t st = c->stream;
+    CK(cudaMallocAsync((void**)&d_xy, sizeof(float) * 2 * (size_t)std::max(vl.m, vr.m), st));
+    CK(cudaMallocAsync((void**)&d_xl, sizeof(double2) * (size_t)vl.m, st));
+    CK(cudaMallocAsync((void**)&d_xr, sizeof(double2) * (size_t)vr.m, st));
+    CK(cudaMallocAsync((void**)&d_out, sizeof(Rec) * (size_t)vl.m, st));
+    CK(cudaMallocAsync((void**)&d_cnt, sizeof(int), st));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    CK(cudaMemcpyAsync(d_xy, vl.xy.data(), sizeof(float) * 2 * (size_t)vl.m, cudaMemcpyHostToDevice, st));
+    positions_to_double_kernel<<<(vl.m + 255) / 256, 256, 0, st>>>(d_xy, vl.m, d_xl);
+    CK(cudaStreamSynchronize(st));                     // d_xy is reused for the right view
+    CK(cudaMemcpyAsync(d_xy, vr.xy.data(), sizeof(float) * 2 * (size_t)vr.m, cudaMemcpyHostToDevice, st));
+    positions_to_double_kernel<<<(vr.m + 255) / 256, 256, 0, st>>>(d_xy, vr.m, d_xr);
+    GuidedParams P;
+    for (int k = 0; k < 9; ++k) P.F[k] = F[k];
+    P.errorTh = errorTh; P.distRatio = distRatio;
+    const int grid = (vl.m + GM_WARPS - 1) / GM_WARPS;
+    CK(cudaEventRecord(c->ev_start, st));
+    if (vl.dtype == DT_F32) guided_top2_kernel<DT_F32><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    else if (vl.dtype == DT_U8) guided_top2_kernel<DT_U8><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    else guided_top2_kernel<DT_BIN><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_end, st));
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<Rec> recs((size_t)n);
+    if (n) CK(cudaMemcpy(recs.data(), d_out, sizeof(Rec) * (size_t)n, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_end));
+    c->last_gpu_ms = ms; c->last_search_ms = ms; c->last_launches = 3; c->last_records = n; c->last_tc_pairs = 0;
+    cudaFreeAsync(d_xy, st); cudaFreeAsync(d_xl, st); cudaFreeAsync(d_xr, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_cnt, st);
+    // IndMatch::getDeduplicated (guidedMatching.hpp:267): one record per left feature, so this is a sort by (i, j)
+    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); });
+    res->matches = c->recycler->take((size_t)std::max(n, 1));
+    for (int k = 0; k < n; ++k) res->matches.p[k] = b200m_match{recs[k].i, recs[k].j, 0.f, 0.f};    // IndMatch(i, j): ratio and distance default to 0
+    res->offsets[1] = n;
+  } else {
+    res->matches = c->recycler->take(1);
+  }
+  *out = res.release();
+  return B200M_OK;
+}
 
 // ---- Surface 2 on several GPUs from ONE process ----------------------------------------------------------------------
 // The reference binary is a single process (main_featureMatching.cpp): to use every GPU of the node behind the same

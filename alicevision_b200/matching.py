@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
     "b200m_shard_pairs", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
-    "b200m_multi_last_gpu_ms",
+    "b200m_multi_last_gpu_ms", "b200m_guided_match",
 ]
 
 
@@ -385,6 +385,35 @@ class ImageCollectionMatcherB200:
             if b > a:
                 out[(i, j)] = matches[a:b]     # view into the engine's result arena
         return out
+
+
+def guidedMatching(F, regions_left: "Regions", regions_right: "Regions", errorTh: float, distRatio: float, ctx: Context | None = None) -> np.ndarray:
+    """matching::guidedMatching<Mat3Model, FundamentalEpipolarDistanceError> (matching/guidedMatching.hpp:206-268) for cameras
+    without distortion: F = 3x3 fundamental matrix (x_right^T F x_left = 0), errorTh / distRatio already squared as at the
+    call site (GeometricFilterMatrix_F_AC.hpp:387-388).  Returns matches[MATCH_DTYPE] with i = left, j = right feature."""
+    ctx = ctx or default_context()
+    lib = ctx.lib
+    ids = (_new_view_id(), _new_view_id())
+    Fm = np.ascontiguousarray(F, np.float64).reshape(9)
+    up = []
+    try:
+        for vid, r in zip(ids, (regions_left, regions_right)):
+            n = r.RegionCount()
+            code = _dtype_code(r.descriptors, r.binary)
+            _check(lib.b200m_upload_view(ctx._h, C.c_uint32(vid), r.descriptors.ctypes.data_as(C.c_void_p) if n else None, C.c_int(n),
+                                         C.c_int(max(r.DescriptorLength(), 1)), C.c_int(code), r.positions.ctypes.data_as(C.c_void_p) if n else None), "b200m_upload_view")
+            up.append(vid)
+        res = C.c_void_p()
+        _check(lib.b200m_guided_match(ctx._h, C.c_uint32(ids[0]), C.c_uint32(ids[1]), Fm.ctypes.data_as(C.c_void_p), C.c_double(errorTh), C.c_double(distRatio),
+                                      C.byref(res)), "b200m_guided_match")
+        owner = _ResultOwner(lib, res)
+        off, mat = C.c_void_p(), C.c_void_p()
+        _check(lib.b200m_result_get(res, None, C.byref(off), C.byref(mat)), "b200m_result_get")
+        n = int(_alias(off.value, 16, np.int64, owner)[1])
+        return _alias(mat.value, n * MATCH_DTYPE.itemsize, MATCH_DTYPE, owner).copy()
+    finally:
+        for vid in up:
+            lib.b200m_remove_view(ctx._h, C.c_uint32(vid))
 
 
 def createImageCollectionMatcher(matcherType: EMatcherType, distRatio: float, crossMatching: bool, ctx: Context | None = None):

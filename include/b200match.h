@@ -109,6 +109,17 @@ int b200m_result_num_pairs(const b200m_result* r);
 int b200m_result_get(const b200m_result* r, const uint32_t** pair_ids, const int64_t** offsets, const b200m_match** matches);
 void b200m_result_free(b200m_result* r);
 
+/* ---- guided matching (the step after the path) ------------------------------------------------------------------------ */
+/* matching::guidedMatching<Mat3Model, FundamentalEpipolarDistanceError>(model, camL, lRegions, camR, rRegions, errorTh,
+ * distRatio, matches) for cameras without distortion (matching/guidedMatching.hpp:206-268; called with
+ * errorTh = Square(precision), distRatio = Square(ratio) by GeometricFilterMatrix_F_AC.hpp:381-389): for every feature of the
+ * LEFT view, among the features of the RIGHT view whose epipolar error (multiview/relativePose/FundamentalError.hpp:52-64,
+ * F row-major, x_right^T F x_left = 0) is below errorTh, the two smallest squared descriptor distances
+ * (Regions::SquaredDescriptorDistance: L2 for scalar, squared Hamming for binary); kept iff best < distRatio * second.
+ * Both views must have been uploaded with positions.  The result holds one pair (view_left, view_right) whose matches are
+ * IndMatch(i = left feature, j = right feature), sorted by (i, j), ratio and distance 0 as in the reference. */
+int b200m_guided_match(b200m_ctx* ctx, uint32_t view_left, uint32_t view_right, const double* F, double errorTh, double distRatio, b200m_result** out);
+
 /* ---- Surface 2 on several GPUs from one process --------------------------------------------------------------------- */
 /* Which shard (0..n_shards-1) each pair goes to: database images (first id) in ascending order are dealt round-robin over
  * the shards, direction alternating every round; all pairs of one database image stay together (its descriptors are

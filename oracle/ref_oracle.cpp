@@ -30,9 +30,11 @@
 #include <aliceVision/feature/Hamming.hpp>
 #include <aliceVision/feature/regionsFactory.hpp>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <random>
 #include <vector>
@@ -151,6 +153,38 @@ static int load_regions_t(const char* featPath, const char* descPath, void* desc
     feats[4 * i] = f.x(); feats[4 * i + 1] = f.y(); feats[4 * i + 2] = f.scale(); feats[4 * i + 3] = f.orientation();
   }
   return n == nf ? n : -2;
+}
+
+
+// ---- guided matching, restated: matching/guidedMatching.hpp:206-268 (cameras == nullptr) with the accumulator :77-118 and the
+// error multiview/relativePose/FundamentalError.hpp:52-64.  The 3x3 Eigen expressions are written out with the association a
+// coefficient-wise evaluation gives (((a+b)+c), separate multiply / add; built with -ffp-contract=off): Eigen itself is not
+// in this image, so THIS sub-expression is unpinned by compiled reference code.  DIST(i, j) is the squared descriptor distance.
+template <class DistFn>
+static int guided_match_loop(const float* xy_l, int n_l, const float* xy_r, int n_r, const double* F, double errorTh, double distRatio, DistFn DIST,
+                             uint32_t* out_ij) {
+  std::vector<std::pair<uint32_t, uint32_t>> out;
+  for (int i = 0; i < n_l; ++i) {
+    const double x0 = (double)xy_l[2 * i], x1 = (double)xy_l[2 * i + 1];                 // GetRegionPosition -> Vec2 (double) of float coordinates
+    const double Fx0 = (F[0] * x0 + F[1] * x1) + F[2] * 1.0, Fx1 = (F[3] * x0 + F[4] * x1) + F[5] * 1.0, Fx2 = (F[6] * x0 + F[7] * x1) + F[8] * 1.0;
+    const double nrm = Fx0 * Fx0 + Fx1 * Fx1;                                            // F_x.head<2>().squaredNorm()
+    double bd = std::numeric_limits<double>::max(), sbd = std::numeric_limits<double>::max(); std::size_t idx = 0;   // distanceRatio(), :86-90
+    for (int j = 0; j < n_r; ++j) {
+      const double y0 = (double)xy_r[2 * j], y1 = (double)xy_r[2 * j + 1];
+      const double dot = (Fx0 * y0 + Fx1 * y1) + Fx2 * 1.0;                              // F_x.dot(y)
+      const double geomErr = (dot * dot) / nrm;                                          // Square(.) / squaredNorm, FundamentalError.hpp:62
+      if (geomErr < errorTh) {                                                           // guidedMatching.hpp:252
+        const double dist = DIST(i, j);
+        if (dist < bd) { idx = (std::size_t)j; sbd = dist; std::swap(bd, sbd); }         // update, :95-110
+        else if (dist < sbd) sbd = dist;
+      }
+    }
+    if (sbd != std::numeric_limits<double>::max() && bd < distRatio * sbd) out.push_back({(uint32_t)i, (uint32_t)idx});   // isValid :115-118, :259-263
+  }
+  std::sort(out.begin(), out.end());                                                     // IndMatch::getDeduplicated, :267
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+  for (size_t k = 0; k < out.size(); ++k) { out_ij[2 * k] = out[k].first; out_ij[2 * k + 1] = out[k].second; }
+  return (int)out.size();
 }
 
 extern "C" {
@@ -310,6 +344,14 @@ int ref_load_desc_u8_as_f32(const char* descPath, float* out, int cap) {
   try { loadDescsFromBinFile<Descriptor<float, 128>, Descriptor<unsigned char, 128>>(descPath, v); } catch (const std::exception&) { return -1; }
   for (int i = 0; i < std::min((int)v.size(), cap); ++i) for (int k = 0; k < 128; ++k) out[(size_t)i * 128 + k] = v[i][k];
   return (int)v.size();
+}
+
+// guided matching with the reference's own Regions::SquaredDescriptorDistance (feature/Regions.hpp:198-207 -> SquaredMetric, :128-141)
+int ref_guided_match(int dtype, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
+                     double errorTh, double distRatio, uint32_t* out_ij) {
+  std::unique_ptr<Regions> rl = make_any_regions(dtype, desc_l, xy_l, n_l), rr = make_any_regions(dtype, desc_r, xy_r, n_r);
+  const Regions* l = rl.get(); const Regions* r = rr.get();
+  return guided_match_loop(xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [l, r](int i, int j) { return l->SquaredDescriptorDistance((size_t)i, r, (size_t)j); }, out_ij);
 }
 
 }  // extern "C"

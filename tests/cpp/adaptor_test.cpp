@@ -8,6 +8,12 @@
 #include <ArrayMatcher_b200.hpp>
 #include <ImageCollectionMatcher_b200.hpp>
 #include <RegionsMatcher_b200.hpp>
+#include <guidedMatching_b200.hpp>
+
+// oracle/_ref/libref_oracle.so: guided-matching loop restated around the reference's Regions::SquaredDescriptorDistance
+extern "C" int ref_guided_match(int dtype, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
+                                double errorTh, double distRatio, uint32_t* out_ij);
+struct Mat3Lite { double v[9]; double operator()(int r, int c) const { return v[3 * r + c]; } };
 
 #include <cstdio>
 #include <random>
@@ -223,6 +229,21 @@ int main()
         }
         delete fa; delete fb; delete ba; delete bb;
         std::printf("RegionsMatcher_b200 (IRegionsMatcher): %zu matches compared\n", compared);
+    }
+    // --- guided matching adaptor (step after the path) vs the oracle loop on the same Regions
+    {
+        const Mat3Lite F{{0, 0, 0, 0, 0, -1, 0, 1, 0}};                  // rectified pair: the epipolar error is (y_r - y_l)^2
+        std::vector<float> xl, xr;
+        for (const auto& f : a->Features()) { xl.push_back(f.x()); xl.push_back(f.y()); }
+        for (const auto& f : b->Features()) { xr.push_back(f.x()); xr.push_back(f.y()); }
+        std::vector<uint32_t> want(2 * a->RegionCount());
+        const int nw = ref_guided_match(1, a->DescriptorRawData(), xl.data(), (int)a->RegionCount(), b->DescriptorRawData(), xr.data(), (int)b->RegionCount(), F.v,
+                                        400.0, 0.81, want.data());
+        IndMatches got;
+        CHECK(guidedMatchingFundamental_b200(F, *a, *b, 400.0, 0.81, got));
+        CHECK(nw > 0 && (int)got.size() == nw);
+        for (int k = 0; k < std::min(nw, (int)got.size()); ++k) CHECK(got[k]._i == want[2 * k] && got[k]._j == want[2 * k + 1]);
+        std::printf("guidedMatchingFundamental_b200: %d matches compared\n", nw);
     }
     std::printf(g_fail ? "ADAPTOR TEST FAILED (%d)\n" : "ADAPTOR TEST PASSED\n", g_fail);
     return g_fail ? 1 : 0;
