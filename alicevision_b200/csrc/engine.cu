@@ -1112,7 +1112,12 @@ int64_t b200m_last_records(const b200m_ctx* c) { return c ? c->last_records : 0;
 
 // ---- guided matching (after the path: GeometricFilterMatrix_F_AC.hpp:363-390 -> matching/guidedMatching.hpp:206-268) ----------------
 int b200m_guided_match(b200m_ctx* c, uint32_t view_left, uint32_t view_right, const double* F, double errorTh, double distRatio, b200m_result** out) {
-  if (!c || !out || !F) return fail(B200M_ERR_ARG, "bad arguments");
+  return b200m_guided_match_model(c, view_left, view_right, B200M_MODEL_FUNDAMENTAL, F, errorTh, distRatio, out);
+}
+
+int b200m_guided_match_model(b200m_ctx* c, uint32_t view_left, uint32_t view_right, int model, const double* F, double errorTh, double distRatio,
+                             b200m_result** out) {
+  if (!c || !out || !F || (model != B200M_MODEL_FUNDAMENTAL && model != B200M_MODEL_HOMOGRAPHY)) return fail(B200M_ERR_ARG, "bad arguments");
   *out = nullptr;
   std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   CK(cudaSetDevice(c->device));
@@ -1145,6 +1150,7 @@ int b200m_guided_match(b200m_ctx* c, uint32_t view_left, uint32_t view_right, co
     CK(cudaMemcpyAsync(d_xy, vr.xy.data(), sizeof(float) * 2 * (size_t)vr.m, cudaMemcpyHostToDevice, st));
     positions_to_double_kernel<<<(vr.m + 255) / 256, 256, 0, st>>>(d_xy, vr.m, d_xr);
     GuidedParams P;
+    P.model = model == B200M_MODEL_HOMOGRAPHY ? GM_HOMOGRAPHY : GM_FUNDAMENTAL;
     for (int k = 0; k < 9; ++k) P.F[k] = F[k];
     P.errorTh = errorTh; P.distRatio = distRatio;
     const int grid = (vl.m + GM_WARPS - 1) / GM_WARPS;

@@ -23,8 +23,11 @@ constexpr int GM_WARPS = 8;          // left features per block
 constexpr int GM_TILE = 1024;        // right positions per shared-memory tile
 constexpr int GM_QUEUE = 40;         // >= 8 + 32: survivors of one 32-wide step appended to at most 7 waiting ones
 
+enum : int { GM_FUNDAMENTAL = 0, GM_HOMOGRAPHY = 1 };
+
 struct GuidedParams {
-  double F[9];          // row-major fundamental matrix: x_right^T F x_left = 0
+  int model;            // GM_FUNDAMENTAL: FundamentalEpipolarDistanceError; GM_HOMOGRAPHY: HomographyAsymmetricError (HomographyError.hpp:23-31)
+  double F[9];          // row-major model matrix: fundamental (x_right^T F x_left = 0) or homography (x_right ~ H x_left)
   double errorTh;       // Square(precision), guidedMatching.hpp:211 / GeometricFilterMatrix_F_AC.hpp:387
   double distRatio;     // Square(distance ratio), :388
 };
@@ -81,6 +84,7 @@ guided_top2_kernel(const void* __restrict__ left, const void* __restrict__ right
     fx1 = __dadd_rn(__dadd_rn(__dmul_rn(P.F[3], x.x), __dmul_rn(P.F[4], x.y)), P.F[5]);
     fx2 = __dadd_rn(__dadd_rn(__dmul_rn(P.F[6], x.x), __dmul_rn(P.F[7], x.y)), P.F[8]);
     nrm = __dadd_rn(__dmul_rn(fx0, fx0), __dmul_rn(fx1, fx1));      // F_x.head<2>().squaredNorm()
+    if (P.model == GM_HOMOGRAPHY) { fx0 = __ddiv_rn(fx0, fx2); fx1 = __ddiv_rn(fx1, fx2); }   // x2_est = x2h_est.head<2>() / x2h_est[2]
   }
   double bd = DBL_MAX, sbd = DBL_MAX; int idx = 0;                   // distanceRatio<double>, guidedMatching.hpp:77-90
   int nq = 0;
@@ -110,8 +114,14 @@ guided_top2_kernel(const void* __restrict__ left, const void* __restrict__ right
       bool pass = false;
       if (e < n) {
         const double2 y = tile[e];
-        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(fx0, y.x), __dmul_rn(fx1, y.y)), fx2);      // F_x.dot((y, 1))
-        const double err = __ddiv_rn(__dmul_rn(dot, dot), nrm);                                       // Square(dot) / squaredNorm
+        double err;
+        if (P.model == GM_HOMOGRAPHY) {
+          const double d0 = __dsub_rn(y.x, fx0), d1 = __dsub_rn(y.y, fx1);                            // (x2 - x2_est).squaredNorm()
+          err = __dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1));
+        } else {
+          const double dot = __dadd_rn(__dadd_rn(__dmul_rn(fx0, y.x), __dmul_rn(fx1, y.y)), fx2);    // F_x.dot((y, 1))
+          err = __ddiv_rn(__dmul_rn(dot, dot), nrm);                                                  // Square(dot) / squaredNorm
+        }
         pass = err < P.errorTh;                                                                       // guidedMatching.hpp:252
       }
       const unsigned m = __ballot_sync(0xffffffffu, pass);

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
     "b200m_shard_pairs", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
-    "b200m_multi_last_gpu_ms", "b200m_guided_match",
+    "b200m_multi_last_gpu_ms", "b200m_guided_match", "b200m_guided_match_model",
 ]
 
 
@@ -387,10 +387,15 @@ class ImageCollectionMatcherB200:
         return out
 
 
-def guidedMatching(F, regions_left: "Regions", regions_right: "Regions", errorTh: float, distRatio: float, ctx: Context | None = None) -> np.ndarray:
+MODEL_FUNDAMENTAL, MODEL_HOMOGRAPHY = 0, 1
+
+
+def guidedMatching(F, regions_left: "Regions", regions_right: "Regions", errorTh: float, distRatio: float, ctx: Context | None = None,
+                   model: int = MODEL_FUNDAMENTAL) -> np.ndarray:
     """matching::guidedMatching<Mat3Model, FundamentalEpipolarDistanceError> (matching/guidedMatching.hpp:206-268) for cameras
     without distortion: F = 3x3 fundamental matrix (x_right^T F x_left = 0), errorTh / distRatio already squared as at the
-    call site (GeometricFilterMatrix_F_AC.hpp:387-388).  Returns matches[MATCH_DTYPE] with i = left, j = right feature."""
+    call site (GeometricFilterMatrix_F_AC.hpp:387-388).  model = MODEL_HOMOGRAPHY: F is a homography and the error is
+    HomographyAsymmetricError (GeometricFilterMatrix_H_AC.hpp:217-225).  Returns matches[MATCH_DTYPE] with i = left, j = right feature."""
     ctx = ctx or default_context()
     lib = ctx.lib
     ids = (_new_view_id(), _new_view_id())
@@ -404,8 +409,8 @@ def guidedMatching(F, regions_left: "Regions", regions_right: "Regions", errorTh
                                          C.c_int(max(r.DescriptorLength(), 1)), C.c_int(code), r.positions.ctypes.data_as(C.c_void_p) if n else None), "b200m_upload_view")
             up.append(vid)
         res = C.c_void_p()
-        _check(lib.b200m_guided_match(ctx._h, C.c_uint32(ids[0]), C.c_uint32(ids[1]), Fm.ctypes.data_as(C.c_void_p), C.c_double(errorTh), C.c_double(distRatio),
-                                      C.byref(res)), "b200m_guided_match")
+        _check(lib.b200m_guided_match_model(ctx._h, C.c_uint32(ids[0]), C.c_uint32(ids[1]), C.c_int(model), Fm.ctypes.data_as(C.c_void_p), C.c_double(errorTh),
+                                            C.c_double(distRatio), C.byref(res)), "b200m_guided_match_model")
         owner = _ResultOwner(lib, res)
         off, mat = C.c_void_p(), C.c_void_p()
         _check(lib.b200m_result_get(res, None, C.byref(off), C.byref(mat)), "b200m_result_get")

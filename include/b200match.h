@@ -119,6 +119,12 @@ void b200m_result_free(b200m_result* r);
  * Both views must have been uploaded with positions.  The result holds one pair (view_left, view_right) whose matches are
  * IndMatch(i = left feature, j = right feature), sorted by (i, j), ratio and distance 0 as in the reference. */
 int b200m_guided_match(b200m_ctx* ctx, uint32_t view_left, uint32_t view_right, const double* F, double errorTh, double distRatio, b200m_result** out);
+/* The same with the model named: B200M_MODEL_FUNDAMENTAL (above) or B200M_MODEL_HOMOGRAPHY = HomographyAsymmetricError
+ * (multiview/relativePose/HomographyError.hpp:23-31: |x_right - (H x_left).head<2>() / (H x_left)[2]|^2), what
+ * GeometricFilterMatrix_H_AC.hpp:217-225 calls. */
+enum { B200M_MODEL_FUNDAMENTAL = 0, B200M_MODEL_HOMOGRAPHY = 1 };
+int b200m_guided_match_model(b200m_ctx* ctx, uint32_t view_left, uint32_t view_right, int model, const double* M, double errorTh, double distRatio,
+                             b200m_result** out);
 
 /* ---- Surface 2 on several GPUs from one process --------------------------------------------------------------------- */
 /* Which shard (0..n_shards-1) each pair goes to: database images (first id) in ascending order are dealt round-robin over

@@ -187,14 +187,14 @@ class Oracle:
 
 
     # -- guided matching (matching/guidedMatching.hpp:206-268, F model, no distortion) ------------------
-    def guided_match(self, desc_l, xy_l, desc_r, xy_r, F, errorTh: float, distRatio: float, binary: bool = False) -> np.ndarray:
+    def guided_match(self, desc_l, xy_l, desc_r, xy_r, F, errorTh: float, distRatio: float, binary: bool = False, model: int = 0) -> np.ndarray:
         """Returns matches[MATCH_DTYPE] (i = left, j = right; ratio = dist = 0 like IndMatch(i, j))."""
         desc_l = np.ascontiguousarray(desc_l); desc_r = np.ascontiguousarray(desc_r)
         xy_l = np.ascontiguousarray(xy_l, np.float32).reshape(-1, 2); xy_r = np.ascontiguousarray(xy_r, np.float32).reshape(-1, 2)
         Fm = np.ascontiguousarray(F, np.float64).reshape(9)
         out = np.zeros((max(desc_l.shape[0], 1), 2), np.uint32)
         f = self._f("guided_match"); f.restype = C.c_int
-        n = f(C.c_int(_dt(desc_l, binary)), _p(desc_l), _p(xy_l), C.c_int(desc_l.shape[0]), _p(desc_r), _p(xy_r), C.c_int(desc_r.shape[0]), _p(Fm),
+        n = f(C.c_int(_dt(desc_l, binary)), C.c_int(model), _p(desc_l), _p(xy_l), C.c_int(desc_l.shape[0]), _p(desc_r), _p(xy_r), C.c_int(desc_r.shape[0]), _p(Fm),
               C.c_double(errorTh), C.c_double(distRatio), _p(out))
         m = np.zeros(n, MATCH_DTYPE)
         m["i"] = out[:n, 0]; m["j"] = out[:n, 1]

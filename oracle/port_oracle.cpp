@@ -166,8 +166,8 @@ int regions_match(int dtype, int hamming, int dim, const void* di, const float* 
 // coefficient-wise evaluation gives (((a+b)+c), separate multiply / add; built with -ffp-contract=off): Eigen itself is not
 // in this image, so THIS sub-expression is unpinned by compiled reference code.  DIST(i, j) is the squared descriptor distance.
 template <class DistFn>
-static int guided_match_loop(const float* xy_l, int n_l, const float* xy_r, int n_r, const double* F, double errorTh, double distRatio, DistFn DIST,
-                             uint32_t* out_ij) {
+static int guided_match_loop(int model, const float* xy_l, int n_l, const float* xy_r, int n_r, const double* F, double errorTh, double distRatio,
+                             DistFn DIST, uint32_t* out_ij) {
   std::vector<std::pair<uint32_t, uint32_t>> out;
   for (int i = 0; i < n_l; ++i) {
     const double x0 = (double)xy_l[2 * i], x1 = (double)xy_l[2 * i + 1];                 // GetRegionPosition -> Vec2 (double) of float coordinates
@@ -176,8 +176,15 @@ static int guided_match_loop(const float* xy_l, int n_l, const float* xy_r, int 
     double bd = std::numeric_limits<double>::max(), sbd = std::numeric_limits<double>::max(); std::size_t idx = 0;   // distanceRatio(), :86-90
     for (int j = 0; j < n_r; ++j) {
       const double y0 = (double)xy_r[2 * j], y1 = (double)xy_r[2 * j + 1];
-      const double dot = (Fx0 * y0 + Fx1 * y1) + Fx2 * 1.0;                              // F_x.dot(y)
-      const double geomErr = (dot * dot) / nrm;                                          // Square(.) / squaredNorm, FundamentalError.hpp:62
+      double geomErr;
+      if (model == 1) {                                                                  // HomographyAsymmetricError, HomographyError.hpp:23-31
+        const double e0 = Fx0 / Fx2, e1 = Fx1 / Fx2;                                     // x2_est = x2h_est.head<2>() / x2h_est[2]
+        const double d0 = y0 - e0, d1 = y1 - e1;
+        geomErr = d0 * d0 + d1 * d1;                                                     // (x2 - x2_est).squaredNorm()
+      } else {
+        const double dot = (Fx0 * y0 + Fx1 * y1) + Fx2 * 1.0;                            // F_x.dot(y)
+        geomErr = (dot * dot) / nrm;                                                     // Square(.) / squaredNorm, FundamentalError.hpp:62
+      }
       if (geomErr < errorTh) {                                                           // guidedMatching.hpp:252
         const double dist = DIST(i, j);
         if (dist < bd) { idx = (std::size_t)j; sbd = dist; std::swap(bd, sbd); }         // update, :95-110
@@ -363,16 +370,16 @@ long port_load_desc(const char* path, void* out, long cap_rows, int row_bytes) {
 
 // guided matching with the restated metrics: SquaredMetric (feature/Regions.hpp:128-141) = L2_Vectorized for scalar regions,
 // SquaredHamming (feature/Hamming.hpp:174-185: h * h in unsigned, returned as double) for binary ones
-int port_guided_match(int dtype, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
+int port_guided_match(int dtype, int model, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
                       double errorTh, double distRatio, uint32_t* out_ij) {
   if (dtype == DT_F32) {
     const float* a = (const float*)desc_l; const float* b = (const float*)desc_r;
-    return guided_match_loop(xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [a, b](int i, int j) { return (double)l2_vec_f32(a + (size_t)i * 128, b + (size_t)j * 128, 128); }, out_ij);
+    return guided_match_loop(model, xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [a, b](int i, int j) { return (double)l2_vec_f32(a + (size_t)i * 128, b + (size_t)j * 128, 128); }, out_ij);
   }
   const uint8_t* a = (const uint8_t*)desc_l; const uint8_t* b = (const uint8_t*)desc_r;
   if (dtype == DT_U8)
-    return guided_match_loop(xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [a, b](int i, int j) { return (double)l2_vec_u8(a + (size_t)i * 128, b + (size_t)j * 128, 128); }, out_ij);
-  return guided_match_loop(xy_l, n_l, xy_r, n_r, F, errorTh, distRatio,
+    return guided_match_loop(model, xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [a, b](int i, int j) { return (double)l2_vec_u8(a + (size_t)i * 128, b + (size_t)j * 128, 128); }, out_ij);
+  return guided_match_loop(model, xy_l, n_l, xy_r, n_r, F, errorTh, distRatio,
                            [a, b](int i, int j) { const uint32_t h = hamming_u8(a + (size_t)i * 64, b + (size_t)j * 64, 64); return (double)(h * h); }, out_ij);
 }
 

@@ -161,8 +161,8 @@ static int load_regions_t(const char* featPath, const char* descPath, void* desc
 // coefficient-wise evaluation gives (((a+b)+c), separate multiply / add; built with -ffp-contract=off): Eigen itself is not
 // in this image, so THIS sub-expression is unpinned by compiled reference code.  DIST(i, j) is the squared descriptor distance.
 template <class DistFn>
-static int guided_match_loop(const float* xy_l, int n_l, const float* xy_r, int n_r, const double* F, double errorTh, double distRatio, DistFn DIST,
-                             uint32_t* out_ij) {
+static int guided_match_loop(int model, const float* xy_l, int n_l, const float* xy_r, int n_r, const double* F, double errorTh, double distRatio,
+                             DistFn DIST, uint32_t* out_ij) {
   std::vector<std::pair<uint32_t, uint32_t>> out;
   for (int i = 0; i < n_l; ++i) {
     const double x0 = (double)xy_l[2 * i], x1 = (double)xy_l[2 * i + 1];                 // GetRegionPosition -> Vec2 (double) of float coordinates
@@ -171,8 +171,15 @@ static int guided_match_loop(const float* xy_l, int n_l, const float* xy_r, int 
     double bd = std::numeric_limits<double>::max(), sbd = std::numeric_limits<double>::max(); std::size_t idx = 0;   // distanceRatio(), :86-90
     for (int j = 0; j < n_r; ++j) {
       const double y0 = (double)xy_r[2 * j], y1 = (double)xy_r[2 * j + 1];
-      const double dot = (Fx0 * y0 + Fx1 * y1) + Fx2 * 1.0;                              // F_x.dot(y)
-      const double geomErr = (dot * dot) / nrm;                                          // Square(.) / squaredNorm, FundamentalError.hpp:62
+      double geomErr;
+      if (model == 1) {                                                                  // HomographyAsymmetricError, HomographyError.hpp:23-31
+        const double e0 = Fx0 / Fx2, e1 = Fx1 / Fx2;                                     // x2_est = x2h_est.head<2>() / x2h_est[2]
+        const double d0 = y0 - e0, d1 = y1 - e1;
+        geomErr = d0 * d0 + d1 * d1;                                                     // (x2 - x2_est).squaredNorm()
+      } else {
+        const double dot = (Fx0 * y0 + Fx1 * y1) + Fx2 * 1.0;                            // F_x.dot(y)
+        geomErr = (dot * dot) / nrm;                                                     // Square(.) / squaredNorm, FundamentalError.hpp:62
+      }
       if (geomErr < errorTh) {                                                           // guidedMatching.hpp:252
         const double dist = DIST(i, j);
         if (dist < bd) { idx = (std::size_t)j; sbd = dist; std::swap(bd, sbd); }         // update, :95-110
@@ -347,11 +354,11 @@ int ref_load_desc_u8_as_f32(const char* descPath, float* out, int cap) {
 }
 
 // guided matching with the reference's own Regions::SquaredDescriptorDistance (feature/Regions.hpp:198-207 -> SquaredMetric, :128-141)
-int ref_guided_match(int dtype, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
+int ref_guided_match(int dtype, int model, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
                      double errorTh, double distRatio, uint32_t* out_ij) {
   std::unique_ptr<Regions> rl = make_any_regions(dtype, desc_l, xy_l, n_l), rr = make_any_regions(dtype, desc_r, xy_r, n_r);
   const Regions* l = rl.get(); const Regions* r = rr.get();
-  return guided_match_loop(xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [l, r](int i, int j) { return l->SquaredDescriptorDistance((size_t)i, r, (size_t)j); }, out_ij);
+  return guided_match_loop(model, xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [l, r](int i, int j) { return l->SquaredDescriptorDistance((size_t)i, r, (size_t)j); }, out_ij);
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@
 #include <guidedMatching_b200.hpp>
 
 // oracle/_ref/libref_oracle.so: guided-matching loop restated around the reference's Regions::SquaredDescriptorDistance
-extern "C" int ref_guided_match(int dtype, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
+extern "C" int ref_guided_match(int dtype, int model, const void* desc_l, const float* xy_l, int n_l, const void* desc_r, const float* xy_r, int n_r, const double* F,
                                 double errorTh, double distRatio, uint32_t* out_ij);
 struct Mat3Lite { double v[9]; double operator()(int r, int c) const { return v[3 * r + c]; } };
 
@@ -237,7 +237,7 @@ int main()
         for (const auto& f : a->Features()) { xl.push_back(f.x()); xl.push_back(f.y()); }
         for (const auto& f : b->Features()) { xr.push_back(f.x()); xr.push_back(f.y()); }
         std::vector<uint32_t> want(2 * a->RegionCount());
-        const int nw = ref_guided_match(1, a->DescriptorRawData(), xl.data(), (int)a->RegionCount(), b->DescriptorRawData(), xr.data(), (int)b->RegionCount(), F.v,
+        const int nw = ref_guided_match(1, 0, a->DescriptorRawData(), xl.data(), (int)a->RegionCount(), b->DescriptorRawData(), xr.data(), (int)b->RegionCount(), F.v,
                                         400.0, 0.81, want.data());
         IndMatches got;
         CHECK(guidedMatchingFundamental_b200(F, *a, *b, 400.0, 0.81, got));

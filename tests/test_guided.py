@@ -56,6 +56,19 @@ def scene(kind, n=1500, seed=7, A=None):
     return dl, xl, dr, xr, truth
 
 
+def homography_scene(kind, n=1200, seed=17):
+    """A planar scene: right positions = H(left) + noise for the re-observed features."""
+    dl, xl, dr, xr, truth = scene(kind, n, seed=seed)
+    xl = (xl * 0.1).astype(np.float32); xr = (xr * 0.1).astype(np.float32)     # a dense 400 x 300 image: several candidates inside the gate
+    H = np.array([[0.96, 0.03, 25.0], [-0.02, 1.02, -14.0], [1.5e-5, -2.0e-5, 1.0]], np.float64)
+    rng = np.random.default_rng(seed + 5)
+    h = np.concatenate([xl.astype(np.float64), np.ones((n, 1))], 1) @ H.T
+    proj = h[:, :2] / h[:, 2:]
+    for i, j in truth.items():
+        xr[j] = (proj[i] + rng.uniform(-1.2, 1.2, 2)).astype(np.float32)
+    return dl, xl, dr, xr, truth, H
+
+
 def kinds():
     return [k for k in ("ref", "port") if oracle.available(k)]
 
@@ -90,6 +103,35 @@ def test_gpu_guided_matching_equals_oracle(kind):
             assert len(got) == len(want) and np.array_equal(got["i"], want["i"]) and np.array_equal(got["j"], want["j"])
             assert not got["ratio"].any() and not got["dist"].any()
         assert len(matching.guidedMatching(F, L, Rr, 4.0, 0.64)) > 300
+
+
+@pytest.mark.skipif(len(kinds()) < 2, reason="needs both the compiled reference and the port")
+def test_port_equals_reference_homography():
+    R, P = oracle.Oracle("ref"), oracle.Oracle("port")
+    for kind in ("u8", "real", "bin"):
+        dl, xl, dr, xr, truth, H = homography_scene(kind, 600)
+        for th, ratio in ((400.0, 0.64), (900.0, 0.36)):
+            a = R.guided_match(dl, xl, dr, xr, H, th, ratio, binary=kind == "bin", model=1); b = P.guided_match(dl, xl, dr, xr, H, th, ratio, binary=kind == "bin", model=1)
+            assert np.array_equal(a, b)
+        a = R.guided_match(dl, xl, dr, xr, H, 400.0, 0.64, binary=kind == "bin", model=1)
+        assert len(a) > 100 and sum(1 for m in a if truth.get(int(m["i"])) == int(m["j"])) > 0.9 * len(a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["u8", "f32", "real", "bin"])
+def test_gpu_guided_matching_homography_equals_oracle(kind):
+    """GeometricFilterMatrix_H_AC.hpp:217-225: guidedMatching<Mat3Model, HomographyAsymmetricError>."""
+    from alicevision_b200 import Regions, matching
+    O = oracle.best()
+    dl, xl, dr, xr, truth, H = homography_scene(kind, 1500)
+    L, Rr = Regions(dl, xl, binary=kind == "bin"), Regions(dr, xr, binary=kind == "bin")
+    for th, ratio in ((400.0, 0.64), (900.0, 0.36), (4.0, 0.64), (1e9, 0.64)):
+        want = O.guided_match(dl, xl, dr, xr, H, th, ratio, binary=kind == "bin", model=1)
+        got = matching.guidedMatching(H, L, Rr, th, ratio, model=matching.MODEL_HOMOGRAPHY)
+        assert len(got) == len(want) and np.array_equal(got["i"], want["i"]) and np.array_equal(got["j"], want["j"])
+    assert len(matching.guidedMatching(H, L, Rr, 400.0, 0.64, model=matching.MODEL_HOMOGRAPHY)) > 300
+    Hbad = H.copy(); Hbad[2] = 0                           # points at infinity: x / 0 -> inf / nan never passes
+    assert len(matching.guidedMatching(Hbad, L, Rr, 400.0, 0.64, model=matching.MODEL_HOMOGRAPHY)) == len(O.guided_match(dl, xl, dr, xr, Hbad, 400.0, 0.64, binary=kind == "bin", model=1)) == 0
 
 
 @pytest.mark.gpu
