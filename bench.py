@@ -150,6 +150,32 @@ def cpu_baseline(descs, xys, pairs, hamming, budget_s):
                       f"{'g++ -O3 -msse2 -fopenmp on the reference headers' if ora.kind == 'ref' else 'C++ port of the reference'}"}
 
 
+def cpu_baseline_cascade(descs, xys, pairs, budget_s):
+    """The reference's CASCADE_HASHING_L2 matcher (matching/ArrayMatcher_cascadeHashing.hpp + CascadeHasher.hpp compiled from the
+    reference tree into oracle/_ref) through the restated collection loop: one hashed database per image I, OpenMP over its J images
+    (ImageCollectionMatcher_generic.cpp:39,68).  Whole database rows of the same pair list until the budget is used.  None when
+    the compiled reference is not available (the port does not restate cascade hashing)."""
+    import oracle
+    if not oracle.available("ref"):
+        return None
+    ora = oracle.Oracle("ref")
+    ora.set_num_threads(host_cores())
+    firsts = np.unique(pairs[:, 0])
+    n = 0; matches = 0
+    t0 = time.perf_counter()
+    for f in firsts:
+        row = pairs[pairs[:, 0] == f]
+        tot, _ = ora.collection_cascade(descs, xys, row, 0.8)
+        n += len(row); matches += tot
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "pairs/s", "cores": ora.num_threads(), "kind": "reference",
+            "sample": f"first {n} pairs (whole database rows) of the same list, {dt:.1f} s, ArrayMatcher_cascadeHashing + ratio test + de-duplication, database "
+                      f"hashed once per image I, OpenMP over J as in ImageCollectionMatcher_generic; {matches} matches; g++ -O3 -msse2 -fopenmp on the "
+                      "reference headers with plain-loop stand-ins for Eigen's MatrixXf/VectorXf (timing baseline, results unpinned)"}
+
+
 def ncu_traffic(kernel_key: str):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -286,8 +312,12 @@ def main():
                                "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_note": tr["note"] if tr else None,
                                "kernel": {1: "tc::l2_top2_tc_kernel", 2: "tc2::l2_top2_tc2_kernel<8,false> (cta_group::2)", 3: "tc2::l2_top2_tc2_kernel<16,false> (cta_group::2)", 4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant], "peak_source": peak_src, "flop_per_pair": flop_pair,
                                "kernel_ms_per_step": ms_search}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # contract: the CPU baseline is timed on rank 0 at N=1 only
             out["cpu_baseline"] = cpu_baseline(descs, xys, pairs, hamming, args.cpu_seconds)
+            if not hamming:                     # the north star also names the reference's cascade-hashing matcher (scalar descriptors only)
+                cb = cpu_baseline_cascade(descs, xys, pairs, max(2.0, args.cpu_seconds / 3))
+                if cb:
+                    out["cpu_baseline_cascade_hashing"] = cb
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

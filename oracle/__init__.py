@@ -186,6 +186,23 @@ class Oracle:
         return res
 
 
+    # -- CASCADE_HASHING_L2 timing baseline (compiled reference only) -----------------------------------
+    def collection_cascade(self, descs, xys, pairs, ratio: float = 0.8, seed: int = 5489):
+        """The reference's ArrayMatcher_cascadeHashing through the restated collection loop (one hashed database per image I,
+        OpenMP over its J images).  Returns (total matches, per-pair counts).  kind "ref" only; timing baseline, results unpinned."""
+        assert self.kind == "ref", "cascade hashing is compiled from the reference headers only"
+        nv = len(descs)
+        descs = [np.ascontiguousarray(d) for d in descs]
+        xys = [np.ascontiguousarray(x, np.float32).reshape(-1, 2) for x in xys]
+        nz = next((d for d in descs if d.shape[0]), descs[0])
+        dptr = (C.c_void_p * nv)(*[d.ctypes.data for d in descs]); xptr = (C.c_void_p * nv)(*[x.ctypes.data for x in xys])
+        nfeat = np.array([d.shape[0] for d in descs], np.int32)
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        counts = np.zeros(max(len(pairs), 1), np.int32)
+        f = self.lib.ref_collection_cascade; f.restype = C.c_long
+        tot = f(C.c_int(_dt(nz, False)), C.c_int(nv), dptr, xptr, _p(nfeat), _p(pairs), C.c_int(len(pairs)), C.c_float(ratio), C.c_uint(seed), _p(counts))
+        return int(tot), counts[: len(pairs)]
+
     # -- guided matching (matching/guidedMatching.hpp:206-268, F model, no distortion) ------------------
     def guided_match(self, desc_l, xy_l, desc_r, xy_r, F, errorTh: float, distRatio: float, binary: bool = False, model: int = 0) -> np.ndarray:
         """Returns matches[MATCH_DTYPE] (i = left, j = right; ratio = dist = 0 like IndMatch(i, j))."""

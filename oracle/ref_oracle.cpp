@@ -9,6 +9,8 @@
 // on the same inputs as the CUDA path.  It is built by oracle/Makefile into
 // oracle/_ref/libref_oracle.so (git-ignored, travels to the GPU box prebuilt).
 //
+// Also compiled verbatim, as a CPU TIMING BASELINE only (the north star names it): matching/ArrayMatcher_cascadeHashing.hpp +
+// matching/CascadeHasher.hpp on top of the shim's plain-loop MatrixXf/VectorXf (not Eigen's kernels => its results are unpinned).
 // Reference code exercised (all verbatim, nothing copied into this repo):
 //   matching/ArrayMatcher_bruteForce.hpp:42-142   Build / SearchNeighbour(s)
 //   feature/metric.hpp:27-139                     L2_Simple, L2_Vectorized (+SSE float)
@@ -22,6 +24,7 @@
 //   matching/RegionsMatcher.cpp:54-176            createRegionsMatcher (4 brute-force cases)
 //   matchingImageCollection/ImageCollectionMatcher_generic.cpp:30-123  the pair loop
 #include <aliceVision/matching/ArrayMatcher_bruteForce.hpp>
+#include <aliceVision/matching/ArrayMatcher_cascadeHashing.hpp>
 #include <aliceVision/matching/RegionsMatcher.hpp>
 #include <aliceVision/matching/IndMatch.hpp>
 #include <aliceVision/matching/IndMatchDecorator.hpp>
@@ -359,6 +362,42 @@ int ref_guided_match(int dtype, int model, const void* desc_l, const float* xy_l
   std::unique_ptr<Regions> rl = make_any_regions(dtype, desc_l, xy_l, n_l), rr = make_any_regions(dtype, desc_r, xy_r, n_r);
   const Regions* l = rl.get(); const Regions* r = rr.get();
   return guided_match_loop(model, xy_l, n_l, xy_r, n_r, F, errorTh, distRatio, [l, r](int i, int j) { return l->SquaredDescriptorDistance((size_t)i, r, (size_t)j); }, out_ij);
+}
+
+// ---- CASCADE_HASHING_L2 through the restated collection loop (ImageCollectionMatcher_generic.cpp:30-123): the matcher (= the hashed
+// database) is built once per database image, and the loop over its J images runs in parallel exactly as the reference enables it
+// for this matcher type (:39,:68 `#pragma omp parallel for schedule(dynamic) if (matcherType == CASCADE_HASHING_L2)`).
+// Returns the total number of matches (or -1); counts[p] per visited pair.  Timing baseline: see the header comment.
+long ref_collection_cascade(int dtype, int n_views, const void* const* desc, const float* const* xy, const int32_t* counts_per_view,
+                            const uint32_t* pairs, int n_pairs, float ratio, unsigned seed, int32_t* counts) {
+  if (dtype == 2) return -1;                                   // RegionsMatcher.cpp:63-64: binary regions need BRUTE_FORCE_HAMMING
+  std::mt19937 rng(seed);
+  std::vector<std::unique_ptr<Regions>> regs(n_views);
+  for (int v = 0; v < n_views; ++v) regs[v] = make_any_regions(dtype, desc[v], xy[v], counts_per_view[v]);
+  PairSet ps;
+  for (int p = 0; p < n_pairs; ++p) ps.insert(Pair(pairs[2 * p], pairs[2 * p + 1]));
+  std::map<size_t, std::vector<size_t>> grouped;
+  for (const Pair& p : ps) grouped[p.first].push_back(p.second);
+  long total = 0; int base = 0;
+  for (auto& g : grouped) {
+    const Regions& regionsI = *regs.at(g.first);
+    const std::vector<size_t>& indexToCompare = g.second;
+    if (regionsI.RegionCount() == 0) { for (size_t j = 0; j < indexToCompare.size(); ++j) counts[base + j] = 0; base += (int)indexToCompare.size(); continue; }
+    std::unique_ptr<IRegionsMatcher> matcher;                  // createRegionsMatcher, RegionsMatcher.cpp:87-92,116-121
+    if (dtype == 1) matcher.reset(new RegionsMatcher<ArrayMatcher_cascadeHashing<unsigned char, L2_Vectorized<unsigned char>>>(rng, regionsI, true));
+    else matcher.reset(new RegionsMatcher<ArrayMatcher_cascadeHashing<float, L2_Vectorized<float>>>(rng, regionsI, true));
+    long sub = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : sub)
+    for (int j = 0; j < (int)indexToCompare.size(); ++j) {
+      const Regions& regionsJ = *regs.at(indexToCompare[j]);
+      IndMatches vec;
+      if (regionsJ.RegionCount() != 0 && regionsI.Type_id() == regionsJ.Type_id()) matcher->Match(ratio, regionsJ, vec);
+      counts[base + j] = (int)vec.size();
+      sub += (long)vec.size();
+    }
+    total += sub; base += (int)indexToCompare.size();
+  }
+  return total;
 }
 
 }  // extern "C"

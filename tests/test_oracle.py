@@ -152,3 +152,24 @@ def test_baseline_config0_cpu_plumbing(oracles):
         assert r.keys() == first.keys() and np.array_equal(r[(0, 1)], first[(0, 1)])
     m = first[(0, 1)]
     assert np.all(m["ratio"] < 0.64 + 1e-6) and np.all(m["i"] < 1000) and np.all(m["j"] < 1000) and len(np.unique(m["i"])) == len(m)
+
+
+@pytest.mark.skipif(not oracle.available("ref"), reason="compiled reference not available")
+def test_cascade_hashing_baseline_compiles_and_agrees_with_brute_force():
+    """The CPU baseline the north star names next to brute force: the reference's ArrayMatcher_cascadeHashing / CascadeHasher
+    compiled from /root/reference (Eigen's dense types replaced by plain-loop stand-ins: timing baseline, results unpinned).
+    An approximate matcher: it must find nearly all of the brute-force matches on well separated synthetic data, and the
+    reference's own empty-array test (matching/matching_test.cpp:156-168) holds."""
+    R = oracle.Oracle("ref")
+    descs, xys = synth.sift_images(3, 1500, np.uint8, seed=8, pool_factor=1.0)
+    pairs = synth.exhaustive_pairs(3)
+    for ds in (descs, [d.astype(np.float32) for d in descs]):
+        tot, counts = R.collection_cascade(ds, xys, pairs, 0.8)
+        bf = R.collection_match(ds, xys, pairs, 0.8)
+        want = np.array([len(bf.get((int(a), int(b)), ())) for a, b in pairs])
+        assert tot == counts.sum() and np.all(counts > 0.9 * want) and np.all(counts <= 1.05 * want + 5)
+    e = [descs[0][:0], descs[1]]
+    tot, counts = R.collection_cascade(e, [xys[0][:0], xys[1]], np.array([[0, 1]]), 0.8)
+    assert tot == 0
+    tot2, counts2 = R.collection_cascade(descs, xys, pairs, 0.8, seed=123)       # another projection: still the same matches, up to a few
+    assert abs(tot2 - R.collection_cascade(descs, xys, pairs, 0.8)[0]) < 0.05 * tot2
