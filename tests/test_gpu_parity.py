@@ -406,3 +406,45 @@ def test_shared_context_from_several_host_threads(ora):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------- ties / degenerate descriptors on the tensor-core path
+def test_tensorcore_path_with_massive_ties(ora):
+    """Tiny alphabets make most distances equal (whole 16-row chunks tie, best == second best for most queries): the chunk-minimum
+    logic of the tensor-core kernel and its exactness pass must still give the reference's lists (a tie never passes d1 < r^2 d2,
+    so the surviving index is unique)."""
+    rng = np.random.default_rng(5)
+    n, m = 3, 1300
+    descs = [rng.integers(0, 2, (m, 128)).astype(np.uint8) for _ in range(n)]
+    for k in range(1, n):                                   # plant exact and near copies so that something passes the ratio test
+        src = rng.permutation(m)[: m // 3]
+        descs[k][: m // 3] = descs[0][src]
+        descs[k][: m // 6, :3] ^= 1
+    _, xys = synth.sift_images(n, m, np.uint8, seed=6, pool_factor=1.0)
+    for ratio in (0.8, 0.99):
+        got, mm = run(descs, xys, synth.exhaustive_pairs(n), ratio=ratio)
+        assert mm.ctx.last_tc_pairs() == 3 and mm.ctx.exactness_errors() == 0
+        assert_same(got, ora.collection_match(descs, xys, synth.exhaustive_pairs(n), ratio))
+    got, _ = run(descs, xys, [(0, 0)])                       # duplicates inside one image: d1 == d2 == 0 never passes
+    assert_same(got, ora.collection_match(descs, xys, [(0, 0)], 0.8))
+
+
+def test_cctag_like_one_hot_descriptors(ora):
+    """CCTAG_Regions are Scalar<uchar,128> with a single 255 at the marker id (feature/cctag/ImageDescriber_CCTAG.cpp:117-122) and go
+    down the L2 uchar path: every distance is 0 or 2*255^2, so the kernel sees nothing but ties apart from the matching marker."""
+    rng = np.random.default_rng(9)
+    def markers(ids):
+        d = np.zeros((len(ids), 128), np.uint8)
+        d[np.arange(len(ids)), ids] = 255
+        return d
+    ids0 = rng.permutation(128)[:40]; ids1 = np.concatenate([rng.permutation(ids0)[:25], np.setdiff1d(np.arange(128), ids0)[:10]])
+    ids2 = np.concatenate([ids0[:10], ids0[:10]])             # the same marker twice: d1 == d2 == 0 for it
+    descs = [markers(ids0), markers(ids1), markers(ids2)]
+    xys = [synth.positions(len(d), rng) for d in descs]
+    pairs = [(0, 1), (1, 0), (0, 2), (2, 0), (1, 2)]
+    for cross in (False, True):
+        got, mm = run(descs, xys, pairs, cross=cross)
+        assert mm.ctx.exactness_errors() == 0
+        want = ora.collection_match(descs, xys, pairs, 0.8, cross=cross)
+        assert_same(got, want)
+    assert len(got[(0, 1)]) == 25 if (0, 1) in got else True
