@@ -10,7 +10,7 @@ from alicevision_b200 import synth, voctree
 ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, default=300); ap.add_argument("--features", type=int, default=8192)
 ap.add_argument("--k", type=int, default=10); ap.add_argument("--levels", type=int, default=4); ap.add_argument("--neighbours", type=int, default=50)
-ap.add_argument("--cpu-images", type=int, default=3); ap.add_argument("--cpu-queries", type=int, default=24)
+ap.add_argument("--cpu-images", type=int, default=3); ap.add_argument("--cpu-queries", type=int, default=24); ap.add_argument("--no-cpu", action="store_true")
 a = ap.parse_args()
 descs, _ = synth.sift_images(a.images, a.features, np.uint8, seed=synth.SEED_DATA, pool_factor=1.0)
 centers, valid = synth.vocabulary_tree(a.k, a.levels, seed=4)
@@ -30,6 +30,8 @@ t4 = time.perf_counter()
 out = {"images": a.images, "features": a.features, "tree": f"K={a.k} L={a.levels} ({a.k ** a.levels} words)", "pairs": int(len(pairs)),
        "gpu": {"populate_ms": 1e3 * (t1 - t0), "tfidf_ms": 1e3 * (t2 - t1), "query_all_ms": 1e3 * (t3 - t2), "scoring_kernels_ms": db.last_gpu_ms(),
                "pair_list_ms": 1e3 * (t4 - t3), "total_ms": 1e3 * (t4 - t0), "images_per_s": a.images / (t4 - t0)}}
+if a.no_cpu:
+    print(json.dumps(out)); sys.exit(0)
 # CPU oracle (compiled reference when present) on a bounded sample, extrapolated
 kind = "ref" if oracle.VoctreeOracle.available("ref") else "port"
 O = oracle.VoctreeOracle(kind)
