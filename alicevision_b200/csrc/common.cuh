@@ -43,7 +43,8 @@ struct PairDev {
   uint32_t mode;             // PM_*
 };
 enum : uint32_t { PM_TC = 0, PM_EXACT_F32 = 1, PM_EXACT_U8 = 2, PM_HAMMING = 3, PM_SKIP = 4,
-                  PM_TC_FUSED = 5 /* tensor-core pair whose kernel also ran the exactness pass: candidates are final */ };
+                  PM_TC_FUSED = 5 /* tensor-core pair whose kernel also ran the exactness pass: candidates are final */,
+                  PM_GENERIC_F32 = 6, PM_GENERIC_U8 = 7 /* scalar descriptors whose length is not 128 (AKAZE float 64, LIOP 144): one warp per query */ };
 
 // Work item of the tensor-core kernel: 128 consecutive queries of pair `pair` against the whole database image.
 struct WorkItem { uint32_t pair, qtile; };

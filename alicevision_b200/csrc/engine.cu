@@ -817,8 +817,8 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
         if (vi.dim != 64) return fail(B200M_ERR_UNSUPPORTED, "binary descriptors must be 64 bytes (AKAZE_BinaryRegions)");
         mode = PM_HAMMING;
       } else {
-        if (vi.dim != 128) return fail(B200M_ERR_UNSUPPORTED, "scalar descriptors must have 128 components on the collection surface");
-        mode = PM_TC;      // provisional: resolved to the tensor-core or an exact kernel once both views' exactness flags are known (enqueue)
+        if (vi.dim != 128) mode = vi.dtype == DT_F32 ? PM_GENERIC_F32 : PM_GENERIC_U8;   // AKAZE float (64), LIOP (144), ...: generic exact path
+        else mode = PM_TC;      // provisional: resolved to the tensor-core or an exact kernel once both views' exactness flags are known (enqueue)
       }
       if (stage == B200M_STAGE_FULL && mode != PM_SKIP && (vi.xy.empty() || vj.xy.empty()))
         return fail(B200M_ERR_ARG, "B200M_STAGE_FULL needs feature positions for every matched view");
@@ -902,7 +902,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
     long tc_rows = 0, tc_n = 0;
     for (int p = 0; p < np; ++p) if (dir[seqv[B.begin + p]].mode == PM_TC) { tc_rows += c->views[dir[seqv[B.begin + p]].slot_i].m; ++tc_n; }
     const bool fused = c->tc_variant >= 2 && tc_n > 0 && tc_rows / tc_n >= 6144;
-    bool any_f32 = false, any_u8 = false, any_ham = false;
+    bool any_f32 = false, any_u8 = false, any_ham = false, any_gf32 = false, any_gu8 = false; int max_qblk_gen = 0;
     for (int p = 0; p < np; ++p) {
       const Directed& d = dir[seqv[B.begin + p]];
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
@@ -915,6 +915,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       if (d.mode == PM_EXACT_F32) { any_f32 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_EXACT_U8) { any_u8 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_HAMMING) { any_ham = true; max_qblk_ham = std::max(max_qblk_ham, (vj.m + HM_TQ - 1) / HM_TQ); }
+      if (d.mode == PM_GENERIC_F32 || d.mode == PM_GENERIC_U8) { (d.mode == PM_GENERIC_F32 ? any_gf32 : any_gu8) = true; max_qblk_gen = std::max(max_qblk_gen, (vj.m + 3) / 4); }
     }
     CK(cudaMemcpyAsync(bb.d_pairs, bb.h_pairs, sizeof(PairDev) * np, cudaMemcpyHostToDevice, c->stream));
     if (n_items) CK(cudaMemcpyAsync(bb.d_items, bb.h_items, sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, c->stream));
@@ -945,6 +946,14 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
     }
     if (any_ham) {
       hamming_top2_kernel<false><<<dim3(max_qblk_ham, np), HM_TQ, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, dist_ratio, nullptr, nullptr);
+      ++launches;
+    }
+    if (any_gf32) {
+      generic_top2_pairs_kernel<float><<<dim3(max_qblk_gen, np), 128, 0, c->stream>>>(c->d_views, bb.d_pairs, PM_GENERIC_F32, bb.d_cands, bb.d_count, ratio_sq);
+      ++launches;
+    }
+    if (any_gu8) {
+      generic_top2_pairs_kernel<uint8_t><<<dim3(max_qblk_gen, np), 128, 0, c->stream>>>(c->d_views, bb.d_pairs, PM_GENERIC_U8, bb.d_cands, bb.d_count, ratio_sq);
       ++launches;
     }
     CK(cudaEventRecord(k1, c->stream));

@@ -203,4 +203,43 @@ generic_knn_kernel(const T* __restrict__ db, int n_db, const T* __restrict__ qs,
   }
 }
 
+// Collection surface for scalar descriptors of any length other than 128 (AKAZE_Float_Regions = float x 64, AKAZE_Liop_Regions =
+// uchar x 144; feature/regionsFactory.hpp:25-27): one warp per query of pair blockIdx.y, L2_Vectorized in the reference's order
+// (gen_dist), two nearest neighbours by (value, index), ratio test, candidate appended.  A functional path, not a tuned one.
+template <typename T>
+__global__ void __launch_bounds__(128)
+generic_top2_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, uint32_t want_mode, Cand* __restrict__ cands,
+                          int* __restrict__ cand_count, float ratio_sq) {
+  const PairDev p = pairs[blockIdx.y];
+  if (p.mode != want_mode) return;
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= (int)p.m_j) return;
+  const int dim = views[p.view_i].dim;
+  const T* db = reinterpret_cast<const T*>(views[p.view_i].raw);
+  const T* qp = reinterpret_cast<const T*>(views[p.view_j].raw) + (size_t)q * dim;
+  uint32_t v1 = 0xFFFFFFFFu, v2 = 0xFFFFFFFFu; int i1 = 0x7fffffff, i2 = 0x7fffffff;
+  for (int r = lane; r < (int)p.m_i; r += 32) {
+    const uint32_t v = __float_as_uint(gen_dist(qp, db + (size_t)r * dim, dim, MET_L2_VECTORIZED));   // non-negative floats order like their bit patterns
+    if (v < v1 || (v == v1 && r < i1)) { v2 = v1; i2 = i1; v1 = v; i1 = r; }
+    else if (v < v2 || (v == v2 && r < i2)) { v2 = v; i2 = r; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {                        // merge two sorted pairs per step
+    const uint32_t a1 = __shfl_xor_sync(0xffffffffu, v1, o), a2 = __shfl_xor_sync(0xffffffffu, v2, o);
+    const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    if (a1 < v1 || (a1 == v1 && j1 < i1)) {
+      if (v1 < a2 || (v1 == a2 && i1 < j2)) { v2 = v1; i2 = i1; } else { v2 = a2; i2 = j2; }
+      v1 = a1; i1 = j1;
+    } else if (a1 < v2 || (a1 == v2 && j1 < i2)) { v2 = a1; i2 = j1; }
+  }
+  if (lane == 0) {
+    const float d1 = __uint_as_float(v1), d2 = __uint_as_float(v2);
+    if (d1 < __fmul_rn(ratio_sq, d2)) {                      // matching/filters.hpp:60
+      const int slot = atomicAdd(&cand_count[blockIdx.y], 1);
+      cands[p.cand_base + slot] = Cand{(uint32_t)q, (uint32_t)i1, d1, d2};
+    }
+  }
+}
+
 }  // namespace b200m

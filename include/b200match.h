@@ -98,6 +98,9 @@ int b200m_clear_views(b200m_ctx* ctx);
 int b200m_remove_view(b200m_ctx* ctx, uint32_t view_id);
 
 /* Match a list of (I, J) view-id pairs: I = database image, J = query image (RegionsMatcher.hpp:157-158).
+ * Scalar descriptors of 128 components take the tensor-core kernel when their values allow it (integers, |v| <= 1024) and the
+ * exact CUDA-core kernel otherwise; other scalar lengths (AKAZE float 64, LIOP uchar 144; regionsFactory.hpp:25-27) take a generic
+ * exact kernel; binary descriptors must be 64 bytes (AKAZE_BinaryRegions).
  * dist_ratio as given on the CLI (main_featureMatching.cpp:102): squared internally for L2, used as is for Hamming.
  * cross != 0 reproduces --crossMatching (ImageCollectionMatcher_generic.cpp:83-111). Pairs are processed and
  * reported in PairSet (lexicographic) order; pairs whose result is empty are reported with zero matches (the adaptor

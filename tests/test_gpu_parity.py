@@ -448,3 +448,39 @@ def test_cctag_like_one_hot_descriptors(ora):
         want = ora.collection_match(descs, xys, pairs, 0.8, cross=cross)
         assert_same(got, want)
     assert len(got[(0, 1)]) == 25 if (0, 1) in got else True
+
+
+# ---------------------------------------------------------------------------------------------- other descriptor lengths
+@pytest.mark.parametrize("kind", ["akaze_float64", "liop_u8_144", "float_130"])
+def test_other_descriptor_lengths_on_the_collection_surface(kind):
+    """AKAZE_Float_Regions (float x 64) and AKAZE_Liop_Regions (uchar x 144) (feature/regionsFactory.hpp:25-27) go through
+    createRegionsMatcher's BRUTE_FORCE_L2 cases like SIFT (RegionsMatcher.cpp:74-79,103-108): generic exact kernel, compared with the
+    restated oracle (the compiled-reference oracle only instantiates the 128 / 64-byte Regions types).  A float length that is not a
+    multiple of 4 makes L2_Vectorized<float> return 0 for every pair (feature/metric.hpp:118-122) -> no match survives."""
+    P = oracle.Oracle("port")
+    rng = np.random.default_rng(12)
+    n, m = 3, 900
+    dim = {"akaze_float64": 64, "liop_u8_144": 144, "float_130": 130}[kind]
+    base = rng.gamma(2.0, 20.0, (m, dim))
+    descs = []
+    for k in range(n):
+        d = base[rng.permutation(m)] + rng.normal(0, 2.5, (m, dim))
+        d[m // 2:] = rng.gamma(2.0, 20.0, (m - m // 2, dim))
+        descs.append(np.clip(d, 0, 255).astype(np.uint8) if kind == "liop_u8_144" else d.astype(np.float32))
+    xys = [synth.positions(m, rng) for _ in range(n)]
+    pairs = synth.exhaustive_pairs(n)
+    for cross in (False, True):
+        got, mm = run(descs, xys, pairs, cross=cross)
+        want = P.collection_match(descs, xys, pairs, 0.8, cross=cross)
+        assert mm.ctx.last_tc_pairs() == 0
+        assert_same(got, want)
+        if kind == "float_130":
+            assert len(got) == 0
+        else:
+            assert len(got) == 3 and all(len(v) > 100 for v in got.values())
+    from alicevision_b200 import Regions, RegionsDatabaseMatcherB200
+    db = RegionsDatabaseMatcherB200(EMatcherType.BRUTE_FORCE_L2_B200, Regions(descs[0], xys[0]))
+    ok, got1 = db.Match(0.8, Regions(descs[1], xys[1]))
+    ok_w, want1 = P.regions_match(descs[0], xys[0], descs[1], xys[1], 0.8, False)
+    assert ok == ok_w
+    assert_same({0: got1}, {0: want1})
