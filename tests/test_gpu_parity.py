@@ -321,6 +321,12 @@ def test_multi_device_single_process(ora, cross):
     got2 = m.Match({i: (descs[i], xys[i]) for i in range(n)}, pairs)      # contexts are reused by the next call
     assert_same(got2, want)
     m.multi.close()
+    # more contexts than database images: some shards are empty
+    m3 = ImageCollectionMatcherB200(0.8, cross, EMatcherType.BRUTE_FORCE_L2_B200, devices=(devices + [devices[0]])[:3] if len(devices) >= 3 else [0, 0, 0])
+    few = [(0, 1), (0, 2), (0, 4)]
+    assert_same(m3.Match({i: (descs[i], xys[i]) for i in range(n)}, few), ora.collection_match(descs, xys, few, 0.8, cross=cross))
+    assert m3.Match({i: (descs[i], xys[i]) for i in range(n)}, np.zeros((0, 2), np.uint32)) == {}
+    m3.multi.close()
 
 
 # ---------------------------------------------------------------------------------------------- more full-size properties
