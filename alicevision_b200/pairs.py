@@ -69,3 +69,28 @@ def savePairsToFile(path: str, pairs: Iterable[Pair]) -> bool:
     with open(path, "w") as f:
         f.write(savePairs(pairs))
     return True
+
+
+# ---- the other pair generators of aliceVision_imageMatching (imageMatching/ImageMatching.cpp:145-189), for plain ids ----------
+def generateSequentialMatches(imagePathPerView: dict, nbMatches: int) -> List[Pair]:
+    """ImageMatching.cpp:145-164: views sorted by image path, each matched with its next nbMatches neighbours; pairs as
+    (min id, max id).  imagePathPerView: {viewId: imagePath}."""
+    order = [v for _, v in sorted((p, int(v)) for v, p in imagePathPerView.items())]
+    out = set()
+    for i in range(len(order)):
+        for n in range(i + 1, min(i + nbMatches + 1, len(order))):
+            a, b = order[i], order[n]
+            out.add((min(a, b), max(a, b)))
+    return sorted(out)
+
+
+def generateAllMatchesInOneMap(viewIds: Iterable[int]) -> List[Pair]:
+    """ImageMatching.cpp:166-186: every pair (a, b) with b > a."""
+    ids = sorted(set(int(v) for v in viewIds))
+    return [(a, b) for k, a in enumerate(ids) for b in ids[k + 1:]]
+
+
+def generateAllMatchesBetweenTwoMap(viewIdsA: Iterable[int], viewIdsB: Iterable[int]) -> List[Pair]:
+    """ImageMatching.cpp:188-206: every (a, b) with a in A and b in B, as given (a may be larger than b, or equal)."""
+    A = sorted(set(int(v) for v in viewIdsA)); B = sorted(set(int(v) for v in viewIdsB))
+    return [(a, b) for a in A for b in B]

@@ -154,3 +154,38 @@ def LoadMatchFile(matches: PairwiseMatches, filepath: str) -> bool:
     finally:
         lib.b200io_matches_free(h)
     return True
+
+
+# ---- the small filters main_featureMatching applies between matching and export (matching/io.cpp:82-130) --------------------
+def filterMatchesByViews(matches: PairwiseMatches, viewsKeys) -> None:
+    """Keep the pairs whose two views are both in viewsKeys (io.cpp:82-93); in place."""
+    keys = set(int(v) for v in viewsKeys)
+    for k in [k for k in matches if k[0] not in keys or k[1] not in keys]:
+        del matches[k]
+
+
+def filterTopMatches(allMatches: PairwiseMatches, maxNum: int, minNum: int) -> None:
+    """io.cpp:95-114: lists shorter than minNum are emptied, lists longer than maxNum truncated (they are already ordered);
+    the (then empty) entries stay in the map, as in the reference."""
+    if maxNum <= 0 and minNum <= 0:
+        return
+    if maxNum > 0 and minNum > maxNum:
+        raise RuntimeError("The minimum number of matches is higher than the maximum.")
+    for perDesc in allMatches.values():
+        for d in list(perDesc):
+            m = perDesc[d]
+            if minNum > 0 and len(m) < minNum:
+                perDesc[d] = m[:0]
+            elif maxNum > 0 and len(m) > maxNum:
+                perDesc[d] = m[:maxNum]
+
+
+def filterMatchesByDesc(allMatches: PairwiseMatches, descTypesFilter) -> None:
+    """io.cpp:116-130: keep only the listed descriptor types; pairs left without any type disappear."""
+    keep = set(descTypesFilter)
+    for k in list(allMatches):
+        kept = {d: m for d, m in allMatches[k].items() if d in keep}
+        if kept:
+            allMatches[k] = kept
+        else:
+            del allMatches[k]

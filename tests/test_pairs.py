@@ -35,3 +35,41 @@ def test_roundtrip_file():
         f = os.path.join(d, "pairsT_IO.txt")
         assert P.savePairsToFile(f, gt)
         assert P.loadPairsFromFile(f) == [(0, 1), (0, 2), (1, 2)]
+
+
+def test_other_pair_generators():
+    """imageMatching/ImageMatching.cpp:145-206 for plain view ids."""
+    from alicevision_b200 import pairs as P
+    paths = {10: "/d/img_003.jpg", 11: "/d/img_001.jpg", 12: "/d/img_002.jpg", 7: "/d/img_004.jpg"}      # path order: 11, 12, 10, 7
+    assert P.generateSequentialMatches(paths, 1) == [(7, 10), (10, 12), (11, 12)]
+    assert P.generateSequentialMatches(paths, 2) == [(7, 10), (7, 12), (10, 11), (10, 12), (11, 12)]
+    assert P.generateSequentialMatches(paths, 0) == [] and P.generateSequentialMatches({}, 3) == []
+    assert P.generateAllMatchesInOneMap([5, 1, 3]) == [(1, 3), (1, 5), (3, 5)] == P.exhaustivePairs([5, 1, 3])
+    assert P.generateAllMatchesBetweenTwoMap([2, 9], [1, 9]) == [(2, 1), (2, 9), (9, 1), (9, 9)]
+
+
+def test_match_filters():
+    """matching/io.cpp:82-130."""
+    import numpy as np
+    import pytest
+    from alicevision_b200 import regions_io as rio
+    from alicevision_b200.matching import MATCH_DTYPE
+    def mk(n):
+        m = np.zeros(n, MATCH_DTYPE); m["i"] = np.arange(n); m["j"] = np.arange(n)[::-1]
+        return m
+    pm = {(0, 1): {"sift": mk(30), "akaze": mk(4)}, (0, 2): {"sift": mk(7)}, (2, 3): {"akaze": mk(50)}}
+    a = {k: dict(v) for k, v in pm.items()}
+    rio.filterMatchesByViews(a, {0, 1, 2})
+    assert sorted(a) == [(0, 1), (0, 2)]
+    b = {k: dict(v) for k, v in pm.items()}
+    rio.filterTopMatches(b, 20, 5)
+    assert len(b[(0, 1)]["sift"]) == 20 and np.array_equal(b[(0, 1)]["sift"]["i"], np.arange(20)) and len(b[(0, 1)]["akaze"]) == 0
+    assert len(b[(0, 2)]["sift"]) == 7 and len(b[(2, 3)]["akaze"]) == 20
+    c = {k: dict(v) for k, v in pm.items()}
+    rio.filterTopMatches(c, 0, 0)
+    assert all(len(c[k][d]) == len(pm[k][d]) for k in pm for d in pm[k])
+    with pytest.raises(RuntimeError):
+        rio.filterTopMatches(c, 5, 10)
+    d = {k: dict(v) for k, v in pm.items()}
+    rio.filterMatchesByDesc(d, ["sift"])
+    assert sorted(d) == [(0, 1), (0, 2)] and list(d[(0, 1)]) == ["sift"]
