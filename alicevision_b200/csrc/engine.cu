@@ -449,6 +449,7 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   CK(cudaEventCreate(&c->ev_start));
   CK(cudaEventCreate(&c->ev_end));
   int ht = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("B200M_HOST_THREADS")) ht = std::max(1, atoi(e));     // several engine processes sharing one host (one per GPU)
   c->pool.reset(new Pool(std::min(std::max(ht, 1), 32)));
   *out = c.release();
   return B200M_OK;

@@ -223,6 +223,12 @@ def main():
     import torch.distributed as dist
     from alicevision_b200 import EMatcherType, ImageCollectionMatcherB200, matching
 
+    if world > 1:
+        # one engine process per GPU shares the host: split the cores between the ranks' finishing pools and keep fewer staging
+        # copies in flight per rank (4 ranks: e2e 160 k -> 178 k pairs/s, profiles/r01d_multi_rank_host_settings.md)
+        os.environ.setdefault("B200M_HOST_THREADS", str(max(4, host_cores() // world)))
+        os.environ.setdefault("B200M_UP_LAG", "6")
+
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
