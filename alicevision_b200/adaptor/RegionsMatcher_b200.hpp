@@ -11,7 +11,7 @@
 
 #include <b200match.h>
 
-#include <ArrayMatcher_b200.hpp>   // b200detail::sharedContext
+#include "ArrayMatcher_b200.hpp"   // b200detail::sharedContext (same directory: matching/)
 
 #include <atomic>
 #include <memory>

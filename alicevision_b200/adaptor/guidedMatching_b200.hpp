@@ -10,7 +10,7 @@
 
 #include <b200match.h>
 
-#include <RegionsMatcher_b200.hpp>   // b200detail::sharedContext / nextViewId / regionsDtype / uploadRegions
+#include "RegionsMatcher_b200.hpp"   // b200detail::sharedContext / nextViewId / regionsDtype / uploadRegions (same directory: matching/)
 
 namespace aliceVision {
 namespace matching {
