@@ -226,7 +226,7 @@ def main():
     if world > 1:
         # one engine process per GPU shares the host: split the cores between the ranks' finishing pools and keep fewer staging
         # copies in flight per rank (4 ranks: e2e 160 k -> 178 k pairs/s, profiles/r01d_multi_rank_host_settings.md)
-        os.environ.setdefault("B200M_HOST_THREADS", str(max(4, host_cores() // world)))
+        os.environ.setdefault("B200M_HOST_THREADS", str(max(12, host_cores() // world)))   # 12 was already too few at 4 ranks
         os.environ.setdefault("B200M_UP_LAG", "6")
 
     torch.cuda.set_device(local)
