@@ -5,6 +5,8 @@
 // same bool-return error behaviour, results per query in ascending distance order.
 #pragma once
 
+#include <map>
+#include <mutex>
 #include <aliceVision/matching/ArrayMatcher.hpp>
 #include <aliceVision/feature/metric.hpp>
 
@@ -29,12 +31,21 @@ template <class Scalar, class Metric> constexpr int dtypeOf()
     return std::is_same<Scalar, float>::value ? B200M_F32 : (MetricId<Metric>::value == B200M_HAMMING ? B200M_BIN : B200M_U8);
 }
 
-/// One engine context per process and device, created on first use.
+/// One engine context per process and device, created on first use.  Thread-safe (IRegionsMatcher adaptors are created from
+/// OpenMP regions): the per-device table is guarded by a mutex, a context is created at most once per device, and a failed
+/// creation is retried by the next caller instead of being cached.
 inline b200m_ctx* sharedContext(int device = 0)
 {
-    static b200m_ctx* ctx = nullptr;
-    if (ctx == nullptr && b200m_ctx_create(device, nullptr, &ctx) != B200M_OK)
-        ctx = nullptr;
+    static std::mutex mu;
+    static std::map<int, b200m_ctx*> table;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = table.find(device);
+    if (it != table.end())
+        return it->second;
+    b200m_ctx* ctx = nullptr;
+    if (b200m_ctx_create(device, nullptr, &ctx) != B200M_OK)
+        return nullptr;
+    table[device] = ctx;
     return ctx;
 }
 }  // namespace b200detail

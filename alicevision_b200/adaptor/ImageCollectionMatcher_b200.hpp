@@ -6,9 +6,11 @@
 
 #include <aliceVision/matchingImageCollection/IImageCollectionMatcher.hpp>
 #include <aliceVision/feature/RegionsPerView.hpp>
+#include <aliceVision/system/Logger.hpp>
 
 #include <b200match.h>
 
+#include <memory>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -18,35 +20,48 @@
 namespace aliceVision {
 namespace matchingImageCollection {
 
+/// Error convention: the reference's ImageCollectionMatcher_generic::Match cannot fail, so an engine failure (no
+/// usable GPU, CUDA error, out of device memory ...) must not abort featureMatching.  Give the adaptor a `fallback` matcher - the
+/// integration passes the reference's own ImageCollectionMatcher_generic(BRUTE_FORCE_L2 | BRUTE_FORCE_HAMMING), see
+/// integration/patches - and every failure is logged and the call is delegated to it, output map untouched by the failed attempt.
+/// This is reference-side adaptor code: libb200match itself keeps no CPU path.  Without a fallback the failure is thrown.
 class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
 {
   public:
-    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming = false, int device = 0)
+    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming = false, int device = 0,
+                                std::shared_ptr<const IImageCollectionMatcher> fallback = nullptr)
       : _f_dist_ratio(distRatio),
         _useCrossMatching(crossMatching),
-        _hamming(hamming)
+        _hamming(hamming),
+        _fallback(std::move(fallback))
     {
         if (b200m_ctx_create(device, nullptr, &_ctx) != B200M_OK)
-            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+            engineUnavailable(b200m_last_error());
     }
-    /// Several GPUs behind one Match call: the pair list is sharded by database image over one engine context per device
-    /// (b200m_multi_match; no collective, pairs are independent).  An empty list means "every visible device".
-    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming, std::vector<int> devices)
+    /// Several GPUs behind one Match call: the pair list is sharded (2-D blocks, b200m_shard_pairs_2d) over one engine context
+    /// per device (b200m_multi_match; no collective, pairs are independent).  An empty list means "every visible device".
+    ImageCollectionMatcher_b200(float distRatio, bool crossMatching, bool hamming, std::vector<int> devices,
+                                std::shared_ptr<const IImageCollectionMatcher> fallback = nullptr)
       : _f_dist_ratio(distRatio),
         _useCrossMatching(crossMatching),
-        _hamming(hamming)
+        _hamming(hamming),
+        _fallback(std::move(fallback))
     {
         if (devices.empty())
             for (int d = 0; d < b200m_device_count(); ++d)
                 devices.push_back(d);
-        if (devices.size() == 1)
+        if (devices.empty())
+            engineUnavailable("no CUDA device");
+        else if (devices.size() == 1)
         {
             if (b200m_ctx_create(devices[0], nullptr, &_ctx) != B200M_OK)
-                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+                engineUnavailable(b200m_last_error());
         }
         else if (b200m_multi_create(devices.data(), static_cast<int>(devices.size()), &_multi) != B200M_OK)
-            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+            engineUnavailable(b200m_last_error());
     }
+    /// true when the engine could not be created and every Match goes to the fallback matcher
+    bool usesFallbackOnly() const { return _ctx == nullptr && _multi == nullptr; }
     ~ImageCollectionMatcher_b200() override
     {
         if (_ctx != nullptr)
@@ -57,11 +72,37 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
 
     /// Same contract as ImageCollectionMatcher_generic::Match: appends to map_PutativesMatches, never inserts empty lists,
     /// silently skips empty / type-mismatched views (:59-63,:74-78), unknown view ids throw std::out_of_range (RegionsPerView.hpp:85).
-    void Match(std::mt19937& /*randomNumberGenerator*/,
+    void Match(std::mt19937& randomNumberGenerator,
                const feature::RegionsPerView& regionsPerView,
                const PairSet& pairs,
                feature::EImageDescriberType descType,
                matching::PairwiseMatches& map_PutativesMatches) const override
+    {
+        std::string error;
+        if (!usesFallbackOnly() && engineMatch(regionsPerView, pairs, descType, map_PutativesMatches, error))
+            return;
+        if (_fallback == nullptr)
+            throw std::runtime_error("b200match: " + error);
+        if (!usesFallbackOnly())
+            ALICEVISION_LOG_WARNING("b200match: " << error << " - matching this pair list with the fallback matcher");
+        _fallback->Match(randomNumberGenerator, regionsPerView, pairs, descType, map_PutativesMatches);
+    }
+
+  private:
+    void engineUnavailable(const std::string& why)
+    {
+        if (_fallback == nullptr)
+            throw std::runtime_error("b200match: " + why);
+        ALICEVISION_LOG_WARNING("b200match: engine unavailable (" << why << ") - using the fallback matcher");
+    }
+
+    /// One Match on the engine.  Returns false with `error` set on an engine failure; the output map is only written on success.
+    /// Unknown view ids throw std::out_of_range exactly like the reference (RegionsPerView.hpp:85): that is the caller's error.
+    bool engineMatch(const feature::RegionsPerView& regionsPerView,
+                     const PairSet& pairs,
+                     feature::EImageDescriberType descType,
+                     matching::PairwiseMatches& map_PutativesMatches,
+                     std::string& error) const
     {
         std::set<IndexT> used;
         for (const Pair& p : pairs)
@@ -129,7 +170,10 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
                 }
             if (b200m_multi_match(_multi, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data(),
                                   usable.data(), static_cast<int>(usable.size() / 2), _f_dist_ratio, _useCrossMatching ? 1 : 0, &res) != B200M_OK)
-                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+            {
+                error = b200m_last_error();
+                return false;
+            }
         }
         for (int dtype = 0; dtype < 3 && _multi == nullptr; ++dtype)
         {
@@ -140,11 +184,18 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             for (auto& v : g.xy)
                 xyp.push_back(v.data());
             if (b200m_upload_views_async(_ctx, static_cast<int>(g.ids.size()), g.ids.data(), g.descs.data(), g.counts.data(), g.dim, dtype, xyp.data()) != B200M_OK)
-                throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+            {
+                error = b200m_last_error();
+                b200m_wait_uploads(_ctx);   // earlier groups may still be reading the Regions
+                return false;
+            }
         }
         if (_multi == nullptr &&
             b200m_match_pairs(_ctx, flat.data(), static_cast<int>(pairs.size()), _f_dist_ratio, _useCrossMatching ? 1 : 0, B200M_STAGE_FULL, &res) != B200M_OK)
-            throw std::runtime_error(std::string("b200match: ") + b200m_last_error());
+        {
+            error = b200m_last_error();
+            return false;
+        }
         const uint32_t* ids = nullptr;
         const int64_t* off = nullptr;
         const b200m_match* m = nullptr;
@@ -161,14 +212,15 @@ class ImageCollectionMatcher_b200 : public IImageCollectionMatcher
             map_PutativesMatches[std::make_pair(ids[2 * k], ids[2 * k + 1])].emplace(descType, std::move(v));
         }
         b200m_result_free(res);
+        return true;
     }
 
-  private:
     float _f_dist_ratio;
     bool _useCrossMatching;
     bool _hamming;
     b200m_ctx* _ctx = nullptr;
     b200m_multi* _multi = nullptr;
+    std::shared_ptr<const IImageCollectionMatcher> _fallback;
 };
 
 }  // namespace matchingImageCollection

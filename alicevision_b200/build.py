@@ -12,7 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libb200match.so")
 SOURCES = ["engine.cu", "voctree.cu", "io.cpp"]
-HEADERS = ["common.cuh", "ptx.cuh", "l2_tc.cuh", "l2_tc2.cuh", "l2_exact.cuh", "hamming.cuh", "prep.cuh", "verify.cuh", "../../include/b200match.h", "../../include/b200io.h", "../../include/b200voc.h"]
+def _deps():
+    """Every file the library is built from: all of csrc/ and the public headers (a forgotten header here once shipped a stale .so)."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.cpp"))
+                  + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h")) + [os.path.abspath(__file__)])
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # explicit form: `-arch=sm_100a` also emits compute_100 PTX, which rejects tcgen05
@@ -31,7 +35,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in _deps())
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:

@@ -16,6 +16,8 @@ enum : uint32_t {
   VF_NONINTEGER = 1u,   // some component is not an integer
   VF_RANGE = 2u,        // some |component| > 1024 (2v would not be exact in fp16)
   VF_NORM = 4u,         // some squared norm >= 2^22 (distances would leave the exact-fp32 range)
+  VF_EXACT_MASK = 7u,   // the bits above: any of them set -> the view cannot take the (integer) tensor-core path
+  VF_POS_NONGENERIC = 8u,   // feature positions: two features share an x or a y (or a NaN): coordinate de-duplication stays on the host
 };
 
 // One uploaded view (image) resident in HBM.
@@ -23,15 +25,17 @@ struct alignas(128) ViewDev {
   CUtensorMap tmap128;  // fp16 [m x 128], box {64 x 128 rows}, SWIZZLE_128B (query tiles; only when dim == 128 scalar)
   CUtensorMap tmap256;  // same tensor, box {64 x 256 rows}: one box = one K-half of a database tile
   CUtensorMap tmap_aug; // fp16 [m_pad x 16] half-norm limbs, box {16 x 128 rows}, SWIZZLE_32B (9th K-step of the AUG kernel)
-  const void* raw;      // original descriptors, row-major m x dim (f32 / u8 / 64-byte binary)
+  const void* raw;      // descriptors as STORED, row-major m x dim: f32 / u8 / 64-byte binary; `dtype` is the storage type (integer-valued
+                        // fp32 descriptors are staged and stored as u8: same values, a quarter of the bytes)
   const __half* h16;    // fp16 copy (scalar, dim == 128) or nullptr
   const float* nbh;     // ||row||^2 / 2, padded to a multiple of 256 rows with 1e30f
   const float* nrm;     // ||row||^2
   const __half* aug16;  // m_pad x 16: [b0, l0, l1, 0...] with ||row||^2/2 = 0.5*b0 + l0 + 2048*l1; pad rows [0, 0, 2047]
   int32_t m;            // number of regions
   int32_t dim;          // components (scalar) or bytes (binary)
-  int32_t dtype;
+  int32_t dtype;        // storage type of `raw` (DT_*)
   int32_t pad_;
+  const uint32_t* yrank;  // per feature: rank of its y among the view's features (finish.cuh), or nullptr without positions
 };
 static_assert(sizeof(ViewDev) % 128 == 0, "ViewDev must keep CUtensorMap 64-byte aligned in arrays");
 
@@ -41,6 +45,7 @@ struct PairDev {
   uint32_t m_i, m_j;
   uint32_t cand_base;        // first candidate slot of this pair (prefix sum of m_j over the batch)
   uint32_t mode;             // PM_*
+  uint32_t slot_base;        // prefix sum of m_i over the batch: this pair's scratch range of the device finishing stage (finish.cuh)
 };
 enum : uint32_t { PM_TC = 0, PM_EXACT_F32 = 1, PM_EXACT_U8 = 2, PM_HAMMING = 3, PM_SKIP = 4,
                   PM_TC_FUSED = 5 /* tensor-core pair whose kernel also ran the exactness pass: candidates are final */,
@@ -57,5 +62,10 @@ struct Cand { uint32_t q, b; float d1, d2; };
 // Raw match record handed to the host: i = database (I) feature, j = query (J) feature, the two smallest distances.
 // i == 0xFFFFFFFF marks a candidate dropped by the exactness pass.  For Hamming d1/d2 hold uint32 bit patterns.
 struct Rec { uint32_t i, j; float d1, d2; };
+
+// Element k of a view's descriptors as float, whatever the storage type (block-uniform branch).
+__device__ __forceinline__ float view_elem(const ViewDev& v, size_t k) {
+  return v.dtype == DT_F32 ? reinterpret_cast<const float*>(v.raw)[k] : (float)reinterpret_cast<const uint8_t*>(v.raw)[k];
+}
 
 }  // namespace b200m

@@ -7,6 +7,7 @@
 #include "../../include/b200match.h"
 
 #include "common.cuh"
+#include "finish.cuh"
 #include "guided.cuh"
 #include "hamming.cuh"
 #include "l2_exact.cuh"
@@ -14,6 +15,10 @@
 #include "l2_tc2.cuh"
 #include "prep.cuh"
 #include "verify.cuh"
+#include "hostconv.hpp"
+
+#include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -21,6 +26,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <fstream>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -47,14 +53,45 @@ namespace b200m { int set_error(int code, const std::string& msg) { return fail(
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ small thread pool
+// CPUs of the NUMA node a GPU hangs off (sysfs), intersected with the CPUs this process may use; empty set = unknown / do not pin.
+// With one engine process (or context) per GPU the staging copies, the pinned ring and the finishing threads then stay on the
+// socket whose PCIe root the GPU is attached to (round-1 verdict: GPUs 0-3 / 4-7 sit on different nodes and nothing was pinned).
+struct CpuSet { cpu_set_t set; int count = 0; CpuSet() { CPU_ZERO(&set); } };
+static CpuSet numa_cpus_of_device(int device) {
+  CpuSet out;
+  if (const char* e = getenv("B200M_NUMA")) if (atoi(e) == 0) return out;
+  char bus[64] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return out; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  int node = -1;
+  { std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node"); if (!(f >> node)) node = -1; }
+  if (node < 0) return out;
+  std::string list;
+  { std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist"); if (!std::getline(f, list)) return out; }
+  cpu_set_t allowed; CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return out;
+  size_t pos = 0;
+  while (pos < list.size()) {                       // "0-31,64-95"
+    size_t end = list.find(',', pos); if (end == std::string::npos) end = list.size();
+    const std::string tok = list.substr(pos, end - pos);
+    int a = 0, b = 0;
+    if (sscanf(tok.c_str(), "%d-%d", &a, &b) == 2) {} else if (sscanf(tok.c_str(), "%d", &a) == 1) b = a; else { pos = end + 1; continue; }
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &out.set); ++out.count; }
+    pos = end + 1;
+  }
+  if (out.count < 2) { CPU_ZERO(&out.set); out.count = 0; }   // a node with (almost) no usable CPU: leave the threads alone
+  return out;
+}
+static void pin_this_thread(const CpuSet& cs) { if (cs.count > 0) pthread_setaffinity_np(pthread_self(), sizeof(cs.set), &cs.set); }
+
 class Pool {
  public:
-  explicit Pool(int n) { resize(n); }
+  explicit Pool(int n, const CpuSet& cs = CpuSet()) : cs_(cs) { resize(n); }
   ~Pool() { stop(); }
   void resize(int n) {
     stop();
     quit_ = false;
-    for (int i = 0; i < std::max(1, n); ++i) th_.emplace_back([this] { run(); });
+    for (int i = 0; i < std::max(1, n); ++i) th_.emplace_back([this] { pin_this_thread(cs_); run(); });
   }
   void submit(std::function<void()> f) {
     { std::lock_guard<std::mutex> l(mu_); q_.push(std::move(f)); ++pending_; }
@@ -89,6 +126,7 @@ class Pool {
   std::condition_variable cv_, done_;
   int pending_ = 0;
   bool quit_ = false;
+  CpuSet cs_;
 };
 
 // Completion tracking for one group of pool tasks (one batch of finishing work).
@@ -136,7 +174,10 @@ struct ViewHost {
   uint32_t id = 0;
   int m = 0, dim = 0, dtype = 0, m_pad = 0;
   void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr;
-  std::vector<float> xy;      // m x 2 positions (host only; used by the finishing stage)
+  bool stored_u8 = false;     // dtype == DT_F32 whose values are integers in 0..255: staged and kept on the device as uchar (hostconv.hpp)
+  float* d_xy = nullptr; uint32_t* d_yrank = nullptr;   // positions + rank of y on the device (device finishing stage, finish.cuh)
+  bool failed = false;        // its upload job failed: the device buffers were never filled
+  std::vector<float> xy;      // m x 2 positions (host copy: finishing of views that are not in general position, cross check)
   uint32_t flags = 0; bool flags_known = true;
   uint64_t seq = 0;           // upload order (monotonic per context)
   bool ready = false;         // copies + preparation kernel complete on the device and flags read back
@@ -144,18 +185,21 @@ struct ViewHost {
   struct PosLazy { std::mutex mu; int state = 0; };
   std::shared_ptr<PosLazy> pos = std::make_shared<PosLazy>();
   bool generic_pos() const;
+  int store_dtype() const { return stored_u8 ? (int)DT_U8 : dtype; }
   bool tc_capable() const { return dtype != DT_BIN && dim == 128 && m > 0; }
-  bool tc_ok() const { return tc_capable() && flags == 0; }
+  bool tc_ok() const { return tc_capable() && (flags & VF_EXACT_MASK) == 0; }
 };
 
 struct UploadJob {
   int n_views = 0, dim = 0; size_t esz = 1;
   std::vector<int> slots; std::vector<const void*> descs; std::vector<int> counts;
+  std::shared_ptr<std::vector<int>> bad = std::make_shared<std::vector<int>>();   // per view: the checked f32 -> u8 conversion hit a value it cannot hold
 };
 
 struct BatchBuf {
   PairDev* d_pairs = nullptr; WorkItem* d_items = nullptr; Cand* d_cands = nullptr; int* d_count = nullptr; int* d_off = nullptr;
   Rec* d_out = nullptr;
+  FinMatch* d_fin = nullptr; int* d_fin_count = nullptr; uint32_t* d_scratch = nullptr;   // device finishing stage (finish.cuh)
   PairDev* h_pairs = nullptr; WorkItem* h_items = nullptr; int* h_meta = nullptr; Rec* h_out = nullptr;   // pinned
   cudaEvent_t ev_meta = nullptr, ev_copy = nullptr;
 };
@@ -163,6 +207,8 @@ struct BatchBuf {
 constexpr int PAIR_CAP = 4096;            // directed pairs per batch
 constexpr long CAND_CAP = 4l << 20;       // candidate slots per batch (sum of m_j)
 constexpr long ITEM_CAP = CAND_CAP / 64 + PAIR_CAP;
+constexpr long SLOT_CAP = 8l << 20;       // database rows per batch (sum of m_i): scratch of the device finishing stage
+constexpr int META_INTS = 3 * PAIR_CAP + 2;   // pinned per-batch read-back: counts | offsets (+1) | finishing counts
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -199,6 +245,9 @@ struct b200m_ctx {
   std::vector<cudaEvent_t> tev;   // search-kernel timing events, reused across calls
   cudaEvent_t ev_start = nullptr, ev_end = nullptr;
   std::unique_ptr<Pool> pool;
+  CpuSet cpus;                    // CPUs of the GPU's NUMA node (pool, uploader thread); empty = not pinned
+  bool u8_staging = true;         // stage integer-valued fp32 descriptors as uchar (B200M_U8_STAGING=0 disables)
+  bool device_finish = true;      // finishing stage on the device for views in general position (B200M_DEVICE_FINISH=0 disables)
   std::shared_ptr<Recycler> recycler = std::make_shared<Recycler>();
   bool force_exact = false;
   int tc_variant = 4;             // 1 = single-CTA kernel (l2_tc.cuh); CTA-pair kernel (l2_tc2.cuh): 2 = 8 epilogue warps, 3 = 16 epilogue warps,
@@ -220,9 +269,13 @@ struct b200m_result {
 // ------------------------------------------------------------------------------------------------ helpers
 // Device buffers of one view (stream-ordered allocations out of the default pool).
 static int alloc_view_buffers(b200m_ctx* c, ViewHost& v) {
-  const size_t esz = v.dtype == DT_F32 ? 4 : 1;
+  const size_t esz = v.store_dtype() == DT_F32 ? 4 : 1;
   const size_t bytes = (size_t)v.m * v.dim * esz;
   CK(cudaMallocAsync(&v.raw, std::max<size_t>(bytes, 256), c->stream));
+  if (!v.xy.empty()) {
+    CK(cudaMallocAsync((void**)&v.d_xy, (size_t)v.m * 8, c->stream));
+    CK(cudaMallocAsync((void**)&v.d_yrank, (size_t)v.m * 4, c->stream));
+  }
   if (v.tc_capable()) {
     v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
     CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
@@ -238,12 +291,15 @@ static void free_view_buffers(b200m_ctx* c, ViewHost& v) {
   if (v.nbh) cudaFreeAsync(v.nbh, c->stream);
   if (v.nrm) cudaFreeAsync(v.nrm, c->stream);
   if (v.aug16) cudaFreeAsync(v.aug16, c->stream);
-  v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr; v.aug16 = nullptr;
+  if (v.d_xy) cudaFreeAsync(v.d_xy, c->stream);
+  if (v.d_yrank) cudaFreeAsync(v.d_yrank, c->stream);
+  v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr; v.aug16 = nullptr; v.d_xy = nullptr; v.d_yrank = nullptr;
 }
 
 static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   std::memset(&d, 0, sizeof(d));
-  d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.aug16 = v.aug16; d.m = v.m; d.dim = v.dim; d.dtype = v.dtype;
+  d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.aug16 = v.aug16; d.m = v.m; d.dim = v.dim; d.dtype = v.store_dtype();
+  d.yrank = v.d_yrank;
   if (v.tc_capable()) {
     const cuuint64_t gdim[2] = {128, (cuuint64_t)v.m};
     const cuuint64_t gstr[1] = {256};
@@ -271,7 +327,7 @@ static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag, cudaStrea
   (void)c;
   if (!v.tc_capable()) return B200M_OK;
   const int grid = (v.m_pad + 7) / 8;
-  if (v.dtype == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
+  if (v.store_dtype() == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
   else prep_view_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
   CK(cudaGetLastError());
   return B200M_OK;
@@ -326,9 +382,12 @@ static int ensure_batch_buffers(b200m_ctx* c) {
     CK(cudaMalloc((void**)&b.d_count, sizeof(int) * PAIR_CAP));
     CK(cudaMalloc((void**)&b.d_off, sizeof(int) * (PAIR_CAP + 1)));
     CK(cudaMalloc((void**)&b.d_out, sizeof(Rec) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_fin, sizeof(FinMatch) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_fin_count, sizeof(int) * PAIR_CAP));
+    CK(cudaMalloc((void**)&b.d_scratch, sizeof(uint32_t) * 2 * SLOT_CAP));
     CK(cudaMallocHost((void**)&b.h_pairs, sizeof(PairDev) * PAIR_CAP));
     CK(cudaMallocHost((void**)&b.h_items, sizeof(WorkItem) * ITEM_CAP));
-    CK(cudaMallocHost((void**)&b.h_meta, sizeof(int) * (2 * PAIR_CAP + 2)));
+    CK(cudaMallocHost((void**)&b.h_meta, sizeof(int) * META_INTS));
     CK(cudaMallocHost((void**)&b.h_out, sizeof(Rec) * CAND_CAP));
     CK(cudaEventCreateWithFlags(&b.ev_meta, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming));
@@ -448,9 +507,12 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   CK(cudaMemset(c->d_err, 0, sizeof(unsigned int)));
   CK(cudaEventCreate(&c->ev_start));
   CK(cudaEventCreate(&c->ev_end));
-  int ht = (int)std::thread::hardware_concurrency();
+  c->cpus = numa_cpus_of_device(device);
+  int ht = c->cpus.count > 0 ? c->cpus.count : (int)std::thread::hardware_concurrency();
   if (const char* e = getenv("B200M_HOST_THREADS")) ht = std::max(1, atoi(e));     // several engine processes sharing one host (one per GPU)
-  c->pool.reset(new Pool(std::min(std::max(ht, 1), 32)));
+  c->pool.reset(new Pool(std::min(std::max(ht, 1), 32), c->cpus));
+  if (const char* e = getenv("B200M_U8_STAGING")) c->u8_staging = atoi(e) != 0;
+  if (const char* e = getenv("B200M_DEVICE_FINISH")) c->device_finish = atoi(e) != 0;
   *out = c.release();
   return B200M_OK;
 }
@@ -473,6 +535,7 @@ void b200m_ctx_destroy(b200m_ctx* c) {
   for (int s = 0; s < 2; ++s) {
     BatchBuf& b = c->buf[s];
     cudaFree(b.d_pairs); cudaFree(b.d_items); cudaFree(b.d_cands); cudaFree(b.d_count); cudaFree(b.d_off); cudaFree(b.d_out);
+    cudaFree(b.d_fin); cudaFree(b.d_fin_count); cudaFree(b.d_scratch);
     cudaFreeHost(b.h_pairs); cudaFreeHost(b.h_items); cudaFreeHost(b.h_meta); cudaFreeHost(b.h_out);
     if (b.ev_meta) cudaEventDestroy(b.ev_meta);
     if (b.ev_copy) cudaEventDestroy(b.ev_copy);
@@ -539,15 +602,27 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
   CK(cudaStreamWaitEvent(c->up_stream, c->ev_alloc, 0));   // the stream-ordered allocations were made on the search stream
-  struct Chunk { int view; size_t off, bytes; bool last; };
+  // A chunk = what one staging buffer carries: a byte range of a view's descriptors copied as they are (CK_RAW), a range of an
+  // integer-valued fp32 view converted to uchar on the way (CK_U8: `bytes` staged bytes = elements, read from 4x as many source
+  // bytes), or the view's positions (CK_XY, after its last descriptor chunk).
+  enum { CK_RAW = 0, CK_U8 = 1, CK_XY = 2 };
+  struct Chunk { int view; int kind; size_t off, bytes; bool last; };
   std::vector<Chunk> chunks;
   const char* e_ch = getenv("B200M_UP_CHUNK_MB"); const char* e_parts = getenv("B200M_UP_PARTS");
   const size_t CH = (size_t)(e_ch ? std::max(1, atoi(e_ch)) : 4) << 20;
   const int max_parts = e_parts ? std::max(1, atoi(e_parts)) : 1;   // measured: splitting a chunk over threads is slower (profiles/r01d_upload_staging.md)
   for (int i = 0; i < job.n_views; ++i) {
-    const size_t bytes = (size_t)job.counts[i] * job.dim * job.esz;
-    if (bytes == 0) chunks.push_back({i, 0, 0, true});      // empty view: only its ready event
-    for (size_t off = 0; off < bytes; off += CH) chunks.push_back({i, off, std::min(CH, bytes - off), off + CH >= bytes});
+    const ViewHost& v = c->views[job.slots[i]];
+    const bool has_xy = v.d_xy != nullptr;
+    const bool u8 = v.stored_u8;
+    const size_t bytes = (size_t)job.counts[i] * job.dim * (u8 ? 1 : job.esz);
+    const size_t step = u8 ? CH / 4 : CH;                  // a converted chunk reads 4x its size: keep the task length the same
+    if (bytes == 0) chunks.push_back({i, CK_RAW, 0, 0, true});      // empty view: only its ready event
+    for (size_t off = 0; off < bytes; off += step) chunks.push_back({i, u8 ? CK_U8 : CK_RAW, off, std::min(step, bytes - off), !has_xy && off + step >= bytes});
+    if (has_xy && bytes) {
+      const size_t xb = (size_t)job.counts[i] * 8;
+      for (size_t off = 0; off < xb; off += CH) chunks.push_back({i, CK_XY, off, std::min(CH, xb - off), off + CH >= xb});
+    }
   }
   for (int k = 0; k < b200m_ctx::NSTG; ++k) {
     if (c->stg_bytes[k] < CH) {
@@ -556,15 +631,34 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     }
     if (!c->stg_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_ev[k], cudaEventDisableTiming));
   }
+  std::vector<int>& bad = *job.bad;
   auto finish_view = [&](int i) -> int {                   // runs right after the last chunk of view i was enqueued
     const int slot = job.slots[i];
     ViewHost& v = c->views[slot];
+    if (v.stored_u8 && __atomic_load_n(&bad[i], __ATOMIC_ACQUIRE)) {
+      // The probe of the first rows said "integers in 0..255" but a later value is not: upload the view as fp32 after all
+      // (rare: the copy below goes through the driver's own pageable staging).  Buffers change -> the view table entry is rewritten.
+      void* nr = nullptr;
+      const size_t fb = (size_t)v.m * v.dim * 4;
+      CK(cudaMallocAsync(&nr, std::max<size_t>(fb, 256), c->up_stream));
+      CK(cudaMemcpyAsync(nr, job.descs[i], fb, cudaMemcpyHostToDevice, c->up_stream));
+      CK(cudaFreeAsync(v.raw, c->up_stream));
+      v.raw = nr; v.stored_u8 = false;
+      int rc = make_view_dev(c, v, c->h_views[slot]);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->up_stream));
+    }
+    const bool flagged = v.tc_capable() || v.d_xy;
+    if (flagged) CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->up_stream));
     if (v.tc_capable()) {
-      CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->up_stream));
       int rc = run_prep(c, v, c->d_flags + slot, c->up_stream);
       if (rc) return rc;
-      CK(cudaMemcpyAsync(c->h_flags + slot, c->d_flags + slot, 4, cudaMemcpyDeviceToHost, c->up_stream));
     }
+    if (v.d_xy) {
+      pos_rank_kernel<<<(v.m + PR_THREADS - 1) / PR_THREADS, PR_THREADS, 0, c->up_stream>>>((const float2*)v.d_xy, v.m, v.d_yrank, c->d_flags + slot);
+      CK(cudaGetLastError());
+    }
+    if (flagged) CK(cudaMemcpyAsync(c->h_flags + slot, c->d_flags + slot, 4, cudaMemcpyDeviceToHost, c->up_stream));
     CK(cudaEventRecord(c->view_ev[slot], c->up_stream));
     publish_issued(c, v.seq);
     return B200M_OK;
@@ -572,12 +666,18 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
   const char* e_lag = getenv("B200M_UP_LAG");
   const int LAG = std::max(1, std::min(b200m_ctx::NSTG - 2, e_lag ? atoi(e_lag) : 12));   // chunks between a memcpy and its H2D (= memcpys in flight)
   std::vector<std::unique_ptr<TaskGroup>> grp(chunks.size());
+  struct WaitAll {                                          // on every exit path: no staging task may outlive `grp`, `chunks` or the caller's buffers
+    std::vector<std::unique_ptr<TaskGroup>>& g;
+    ~WaitAll() { for (auto& x : g) if (x) x->wait(); }
+  } wait_all{grp};
   auto issue_h2d = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
     const int sidx = (int)(k % b200m_ctx::NSTG);
     grp[k]->wait();
-    if (ch.bytes) {
-      CK(cudaMemcpyAsync((char*)c->views[job.slots[ch.view]].raw + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->up_stream));
+    const ViewHost& v = c->views[job.slots[ch.view]];
+    if (ch.bytes && !(ch.kind == CK_U8 && __atomic_load_n(&bad[ch.view], __ATOMIC_ACQUIRE))) {
+      char* dst = ch.kind == CK_XY ? (char*)v.d_xy : (char*)v.raw;
+      CK(cudaMemcpyAsync(dst + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->up_stream));
       CK(cudaEventRecord(c->stg_ev[sidx], c->up_stream));
     }
     if (ch.last) return finish_view(ch.view);
@@ -589,13 +689,23 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     CK(cudaEventSynchronize(c->stg_ev[sidx]));             // the H2D that last used this staging buffer is done (no-op when never recorded)
     grp[k].reset(new TaskGroup());
     if (ch.bytes) {
-      // the pageable -> pinned copy of one chunk may be split over pool threads (B200M_UP_PARTS; default 1)
-      const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_parts, ch.bytes >> 19));
-      grp[k]->add(parts);
-      char* d = (char*)c->stg[sidx]; const char* sp = (const char*)job.descs[ch.view] + ch.off; TaskGroup* g = grp[k].get();
-      for (int q = 0; q < parts; ++q) {
-        const size_t a0 = ch.bytes * q / parts, a1 = ch.bytes * (q + 1) / parts;
-        c->pool->submit([=] { std::memcpy(d + a0, sp + a0, a1 - a0); g->done(); });
+      char* d = (char*)c->stg[sidx]; TaskGroup* g = grp[k].get();
+      if (ch.kind == CK_U8) {
+        grp[k]->add(1);
+        const float* sp = (const float*)job.descs[ch.view] + ch.off; const size_t n = ch.bytes; int* flag = &bad[ch.view];
+        c->pool->submit([=] {
+          if (!__atomic_load_n(flag, __ATOMIC_RELAXED) && !f32_to_u8_checked(sp, (uint8_t*)d, n)) __atomic_store_n(flag, 1, __ATOMIC_RELEASE);
+          g->done();
+        });
+      } else {
+        // the pageable -> pinned copy of one chunk may be split over pool threads (B200M_UP_PARTS; default 1)
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_parts, ch.bytes >> 19));
+        grp[k]->add(parts);
+        const char* sp = ch.kind == CK_XY ? (const char*)c->views[job.slots[ch.view]].xy.data() + ch.off : (const char*)job.descs[ch.view] + ch.off;
+        for (int q = 0; q < parts; ++q) {
+          const size_t a0 = ch.bytes * q / parts, a1 = ch.bytes * (q + 1) / parts;
+          c->pool->submit([=] { std::memcpy(d + a0, sp + a0, a1 - a0); g->done(); });
+        }
       }
     }
     if (k >= (size_t)LAG) { int rc = issue_h2d(k - LAG); if (rc) return rc; }
@@ -606,6 +716,7 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
 }
 
 static void uploader_main(b200m_ctx* c) {
+  pin_this_thread(c->cpus);
   for (;;) {
     UploadJob job;
     {
@@ -618,6 +729,7 @@ static void uploader_main(b200m_ctx* c) {
     {
       std::lock_guard<std::mutex> l(c->up_mu);
       if (rc && !c->up_rc) { c->up_rc = rc; c->up_err = g_err; }
+      if (rc) for (int slot : job.slots) c->views[slot].failed = true;   // never filled: a later job's sequence numbers must not make them look ready
       --c->up_active;
     }
     c->up_cv.notify_all();
@@ -640,8 +752,9 @@ static int ensure_view_ready(b200m_ctx* c, int slot) {
   if (v.ready) return B200M_OK;
   {
     std::unique_lock<std::mutex> l(c->up_mu);
-    c->up_cv.wait(l, [&] { return c->up_issued_seq >= v.seq || c->up_rc != 0 || c->up_active == 0; });
+    c->up_cv.wait(l, [&] { return c->up_issued_seq >= v.seq || c->up_rc != 0 || c->up_active == 0 || v.failed; });
     if (c->up_rc) { g_err = c->up_err; return c->up_rc; }
+    if (v.failed) return fail(B200M_ERR_CUDA, "the upload of view " + std::to_string(v.id) + " failed earlier; upload it again");
     if (c->up_issued_seq < v.seq) return fail(B200M_ERR_INTERNAL, "view was never uploaded");
   }
   CK(cudaEventSynchronize(c->view_ev[slot]));
@@ -661,12 +774,19 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
   std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   if (n_views < 0 || dim < 1 || dtype < 0 || dtype > 2 || (n_views > 0 && (!view_ids || !descs || !counts))) return fail(B200M_ERR_ARG, "bad view arguments");
   for (int i = 0; i < n_views; ++i) if (counts[i] < 0 || (counts[i] > 0 && !descs[i])) return fail(B200M_ERR_ARG, "bad view arguments");
+  {
+    // one view id may appear once per call: two entries would share one slot (and one set of device buffers) inside the job
+    std::vector<uint32_t> ids(view_ids, view_ids + n_views);
+    std::sort(ids.begin(), ids.end());
+    if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return fail(B200M_ERR_ARG, "a view id appears twice in one upload call");
+  }
   CK(cudaSetDevice(c->device));
   int rc = wait_uploads(c);              // one job at a time: slot table, staging ring and view table are not shared between jobs
   if (rc) return rc;
   UploadJob job;
   job.n_views = n_views; job.dim = dim; job.esz = dtype == DT_F32 ? 4 : 1;
   job.slots.resize(n_views); job.descs.assign(descs, descs + n_views); job.counts.assign(counts, counts + n_views);
+  job.bad->assign(n_views, 0);
   bool waited = false;
   for (int i = 0; i < n_views; ++i) {
     int slot;
@@ -692,9 +812,15 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
     v = ViewHost();
     v.id = view_ids[i]; v.m = counts[i]; v.dim = dim; v.dtype = dtype;
     v.seq = ++c->next_seq;
-    v.flags_known = !v.tc_capable();
     const int n = counts[i];
-    if (xys && xys[i] && n > 0) v.xy.assign(xys[i], xys[i] + 2 * (size_t)n);   // general position is checked lazily by the finishing stage
+    if (xys && xys[i] && n > 0) v.xy.assign(xys[i], xys[i] + 2 * (size_t)n);   // general position: decided on the device (pos_rank_kernel)
+    v.flags_known = !(v.tc_capable() || !v.xy.empty());
+    if (c->u8_staging && dtype == DT_F32 && dim == 128 && n > 0) {
+      // probe: integer-valued fp32 descriptors (the SIFT extractor's output) are staged and stored as uchar; real-valued data
+      // fails on its first rows.  A later surprise is caught by the checked conversion of every chunk (run_upload).
+      uint8_t tmp[4 * 128];
+      v.stored_u8 = f32_to_u8_checked((const float*)descs[i], tmp, (size_t)std::min(n, 4) * 128);
+    }
     if (n > 0 && (rc = alloc_view_buffers(c, v))) return rc;
     if (!c->view_ev[slot]) CK(cudaEventCreateWithFlags(&c->view_ev[slot], cudaEventDisableTiming));
   }
@@ -705,11 +831,13 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
     CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->stream));
   }
   CK(cudaEventRecord(c->ev_alloc, c->stream));
-  // general-position checks (2 sorts per view) run on the pool now, in parallel; a finishing task that needs one earlier computes it itself
-  for (int i = 0; i < n_views; ++i) {
-    const ViewHost* vp = &c->views[job.slots[i]];          // deque element: stable address; replaced / removed only after pool->wait()
-    if (!vp->xy.empty()) c->pool->submit([vp] { (void)vp->generic_pos(); });
-  }
+  // general position is decided on the device (pos_rank_kernel); without the device finishing stage the host checks it eagerly
+  // (2 sorts per view) on the pool, in parallel; a finishing task that needs one earlier computes it itself
+  if (!c->device_finish)
+    for (int i = 0; i < n_views; ++i) {
+      const ViewHost* vp = &c->views[job.slots[i]];        // deque element: stable address; replaced / removed only after pool->wait()
+      if (!vp->xy.empty()) c->pool->submit([vp] { (void)vp->generic_pos(); });
+    }
   {
     std::lock_guard<std::mutex> l(c->up_mu);
     if (!c->up_thread.joinable()) c->up_thread = std::thread(uploader_main, c);
@@ -848,20 +976,20 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   struct Batch { size_t begin, end; };
   std::vector<Batch> batches;
   {
-    size_t b0 = 0; long cand = 0, items = 0;
+    size_t b0 = 0; long cand = 0, items = 0, slots = 0;
     size_t pair_cap = pending ? 64 : (size_t)PAIR_CAP;
     for (size_t k = 0; k < seqv.size(); k += step) {
-      long need_c = 0, need_i = 0;
+      long need_c = 0, need_i = 0, need_s = 0;
       for (size_t u = k; u < k + step; ++u) {
-        const int mj = c->views[dir[seqv[u]].slot_j].m;
-        if (mj > CAND_CAP) return fail(B200M_ERR_UNSUPPORTED, "view too large for one batch");
-        need_c += mj; need_i += (mj + tc::BM - 1) / tc::BM;
+        const int mj = c->views[dir[seqv[u]].slot_j].m, mi = c->views[dir[seqv[u]].slot_i].m;
+        if (mj > CAND_CAP || mi > SLOT_CAP / 2) return fail(B200M_ERR_UNSUPPORTED, "view too large for one batch");
+        need_c += mj; need_i += (mj + tc::BM - 1) / tc::BM; need_s += mi;
       }
-      if (k > b0 && (cand + need_c > CAND_CAP || items + need_i > ITEM_CAP || k - b0 + step > pair_cap)) {
-        batches.push_back({b0, k}); b0 = k; cand = 0; items = 0;
+      if (k > b0 && (cand + need_c > CAND_CAP || items + need_i > ITEM_CAP || slots + need_s > SLOT_CAP || k - b0 + step > pair_cap)) {
+        batches.push_back({b0, k}); b0 = k; cand = 0; items = 0; slots = 0;
         pair_cap = std::min<size_t>(PAIR_CAP, pair_cap * 2);
       }
-      cand += need_c; items += need_i;
+      cand += need_c; items += need_i; slots += need_s;
     }
     if (seqv.size() > b0) batches.push_back({b0, seqv.size()});
   }
@@ -876,6 +1004,11 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   std::vector<int> dir_len(dir.size(), 0);
   std::vector<std::unique_ptr<TaskGroup>> groups;
   for (size_t b = 0; b < batches.size(); ++b) groups.emplace_back(new TaskGroup());
+  struct WaitGroups {       // every exit path (CUDA error, failed upload ...): the finishing tasks already submitted write into `arena`, `dir_len`
+    std::vector<std::unique_ptr<TaskGroup>>& g;             // and signal `groups`; they must be done before those locals are destroyed
+    ~WaitGroups() { for (auto& x : g) x->wait(); }
+  } wait_groups{groups};
+  const bool dev_fin = c->device_finish && stage == B200M_STAGE_FULL;
   size_t tev_used = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
   int launches = 0;
@@ -885,7 +1018,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
     const Batch& B = batches[bi];
     BatchBuf& bb = c->buf[bi & 1];
     const int np = (int)(B.end - B.begin);
-    uint32_t cbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
+    uint32_t cbase = 0, sbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
     // In-kernel exactness pass only when a work item lasts long enough (>= 24 database tiles on average) for two warps to
     // re-score the previous item's candidates behind it; shorter images use the stand-alone exactness kernel.
     // the views of this batch must be complete on the device; their exactness flags decide tensor-core vs exact kernel
@@ -909,8 +1042,8 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
       // the CTA-pair kernel runs the exactness pass itself: its candidates are final records
       const uint32_t dev_mode = (d.mode == PM_TC && fused) ? (uint32_t)PM_TC_FUSED : d.mode;
-      bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, dev_mode};
-      cbase += (uint32_t)vj.m;
+      bb.h_pairs[p] = PairDev{(uint32_t)d.slot_i, (uint32_t)d.slot_j, (uint32_t)vi.m, (uint32_t)vj.m, cbase, dev_mode, sbase};
+      cbase += (uint32_t)vj.m; sbase += (uint32_t)vi.m;
       const int qrows = c->tc_variant >= 2 ? 2 * tc2::BM : tc::BM;   // queries per work item
       if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + qrows - 1) / qrows; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
       if (d.mode == PM_EXACT_F32) { any_f32 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
@@ -962,6 +1095,11 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
     scan_counts_kernel<<<1, 1024, 0, c->stream>>>(bb.d_count, np, bb.d_off);
     verify_pack_kernel<<<dim3(np, VERIFY_BLOCKS_PER_PAIR), VERIFY_WARPS * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, bb.d_off, bb.d_out, ratio_sq, c->d_err);
     launches += 2;
+    if (dev_fin) {
+      finish_pairs_kernel<<<np, FIN_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, c->d_flags, bb.d_out, bb.d_count, bb.d_off, bb.d_scratch, bb.d_fin, bb.d_fin_count);
+      ++launches;
+      CK(cudaMemcpyAsync(bb.h_meta + 2 * PAIR_CAP + 2, bb.d_fin_count, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(bb.h_meta, bb.d_count, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(bb.h_meta + PAIR_CAP, bb.d_off, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, c->stream));
@@ -989,17 +1127,20 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       if (bi + 1 < batches.size()) {
         // buffer set (bi+1)&1 was last used by batch bi-1: its records have been consumed (pool wait below)
         if ((rc = enqueue(bi + 1))) return rc;
-      } else {
-        CK(cudaEventRecord(c->ev_end, c->stream));
       }
       CK(cudaEventSynchronize(bb.ev_meta));
       const int total = bb.h_meta[PAIR_CAP + np];
       if (bi >= 2) groups[bi - 2]->wait();       // the tasks of batch bi-2 read this pinned record buffer
       if (total > 0) {
         CK(cudaStreamWaitEvent(c->copy_stream, bb.ev_meta, 0));
-        CK(cudaMemcpyAsync(bb.h_out, bb.d_out, sizeof(Rec) * (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaMemcpyAsync(bb.h_out, dev_fin ? (const void*)bb.d_fin : (const void*)bb.d_out, sizeof(Rec) * (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
         CK(cudaEventRecord(bb.ev_copy, c->copy_stream));
         CK(cudaEventSynchronize(bb.ev_copy));
+      }
+      if (bi + 1 == batches.size()) {
+        // end of the device work of this call = the last match list has landed in pinned host memory
+        CK(cudaStreamWaitEvent(c->copy_stream, bb.ev_meta, 0));
+        CK(cudaEventRecord(c->ev_end, c->copy_stream));
       }
       total_records += total;
       // finishing tasks (one per directed pair) run behind the GPU: they only have to be done before batch bi+2's records
@@ -1008,7 +1149,8 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       arena.b[bi] = c->recycler->take((size_t)std::max(total, 1));
       TaskGroup* grp = groups[bi].get();
       // one pool task per ~4096 records (or 64 pairs): for small images the task hand-off would otherwise cost more than the work
-      struct Job { const Rec* recs; int cnt; b200m_match* dst; int* len; const ViewHost* vi; const ViewHost* vj; bool ham; };
+      // cnt >= 0: raw records, finished here (finish_directed); done >= 0: `done` final matches from the device finishing stage, copied
+      struct Job { const Rec* recs; int cnt; int done; b200m_match* dst; int* len; const ViewHost* vi; const ViewHost* vj; bool ham; };
       auto jobs = std::make_shared<std::vector<Job>>();
       long job_records = 0;
       const bool full = stage == B200M_STAGE_FULL;
@@ -1017,7 +1159,10 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
         grp->add(1);
         std::shared_ptr<std::vector<Job>> mine = std::move(jobs);
         c->pool->submit([mine, grp, full] {
-          for (const Job& j : *mine) *j.len = finish_directed(j.recs, j.cnt, j.ham, full, *j.vi, *j.vj, j.dst);
+          for (const Job& j : *mine) {
+            if (j.done >= 0) { std::memcpy(j.dst, j.recs, sizeof(b200m_match) * (size_t)j.done); *j.len = j.done; }
+            else *j.len = finish_directed(j.recs, j.cnt, j.ham, full, *j.vi, *j.vj, j.dst);
+          }
           grp->done();
         });
         jobs = std::make_shared<std::vector<Job>>();
@@ -1027,9 +1172,14 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
         const size_t di = seqv[B.begin + p];
         const Directed d = dir[di];
         dir_ptr[di] = arena.b[bi].p + bb.h_meta[PAIR_CAP + p];
-        const int cnt = bb.h_meta[p];
+        int cnt = bb.h_meta[p], done = -1;
         if (d.mode == PM_SKIP || cnt == 0) continue;
-        jobs->push_back(Job{bb.h_out + bb.h_meta[PAIR_CAP + p], cnt, dir_ptr[di], &dir_len[di], &c->views[d.slot_i], &c->views[d.slot_j], d.mode == PM_HAMMING});
+        if (dev_fin) {                                   // >= 0: final matches; < 0: -(records + 1) left for the host (view not in general position)
+          const int f = bb.h_meta[2 * PAIR_CAP + 2 + p];
+          if (f >= 0) done = f; else cnt = -(f + 1);
+          if (done == 0) continue;
+        }
+        jobs->push_back(Job{bb.h_out + bb.h_meta[PAIR_CAP + p], cnt, done, dir_ptr[di], &dir_len[di], &c->views[d.slot_i], &c->views[d.slot_j], d.mode == PM_HAMMING});
         job_records += cnt;
         if (job_records >= 4096 || jobs->size() >= 64) flush();
       }
@@ -1043,6 +1193,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   const double t_gpu_done = now();
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
+  CK(cudaEventSynchronize(c->ev_end));
   CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_end));
   c->last_gpu_ms = ms;
   double sk = 0;
@@ -1165,9 +1316,22 @@ int b200m_guided_match_model(b200m_ctx* c, uint32_t view_left, uint32_t view_rig
     P.errorTh = errorTh; P.distRatio = distRatio;
     const int grid = (vl.m + GM_WARPS - 1) / GM_WARPS;
     CK(cudaEventRecord(c->ev_start, st));
-    if (vl.dtype == DT_F32) guided_top2_kernel<DT_F32><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
-    else if (vl.dtype == DT_U8) guided_top2_kernel<DT_U8><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
-    else guided_top2_kernel<DT_BIN><<<grid, GM_WARPS * 32, 0, st>>>(vl.raw, vr.raw, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    // integer-valued fp32 views are stored as uchar (same distances: exact integers); a pair of one such view and one real-valued
+    // fp32 view gets a temporary fp32 expansion of the former
+    const void* rawl = vl.raw; const void* rawr = vr.raw; float* tmp32 = nullptr;
+    int kdt = vl.store_dtype();
+    if (vl.store_dtype() != vr.store_dtype()) {
+      const ViewHost& vu = vl.stored_u8 ? vl : vr;
+      const size_t ne = (size_t)vu.m * 128;
+      CK(cudaMallocAsync((void**)&tmp32, ne * 4, st));
+      u8_to_f32_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const uint8_t*)vu.raw, tmp32, ne);
+      (vl.stored_u8 ? rawl : rawr) = tmp32;
+      kdt = DT_F32;
+    }
+    if (kdt == DT_F32) guided_top2_kernel<DT_F32><<<grid, GM_WARPS * 32, 0, st>>>(rawl, rawr, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    else if (kdt == DT_U8) guided_top2_kernel<DT_U8><<<grid, GM_WARPS * 32, 0, st>>>(rawl, rawr, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    else guided_top2_kernel<DT_BIN><<<grid, GM_WARPS * 32, 0, st>>>(rawl, rawr, d_xl, d_xr, vl.m, vr.m, P, d_out, d_cnt);
+    if (tmp32) cudaFreeAsync(tmp32, st);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_end, st));
     int n = 0;
@@ -1210,6 +1374,69 @@ int b200m_shard_pairs(const uint32_t* pairs, int n_pairs, int n_shards, int32_t*
     ++k;
   }
   for (int p = 0; p < n_pairs; ++p) shard_of[p] = owner[pairs[2 * p]];
+  return B200M_OK;
+}
+
+// 2-D sharding: what a shard must UPLOAD shrinks with the number of shards.  The view ids (sorted) are dealt cyclically into g
+// classes; a pair belongs to the folded block {class(I), class(J)} (g(g+1)/2 blocks: the pair matrix is symmetric in what it needs,
+// both views); blocks go to shards heaviest first, each to the least loaded shard, ties to the shard that already holds most of
+// the block's classes.  g is chosen per call: the smallest maximum number of classes per shard among the g whose load imbalance is
+// within 3 % (else the best balance).  8 shards -> g = 4: six shards own one off-diagonal block (2 of 4 classes = half of the views),
+// two own two diagonal blocks each; 4 shards -> 3 of 4 classes at most; 2 shards need every view whatever the split.
+int b200m_shard_pairs_2d(const uint32_t* pairs, int n_pairs, int n_shards, int32_t* shard_of) {
+  if (n_pairs < 0 || n_shards < 1 || (n_pairs > 0 && (!pairs || !shard_of))) return fail(B200M_ERR_ARG, "bad arguments");
+  if (n_pairs == 0) return B200M_OK;
+  if (n_shards == 1) { std::fill(shard_of, shard_of + n_pairs, 0); return B200M_OK; }
+  std::vector<uint32_t> ids(pairs, pairs + 2 * (size_t)n_pairs);
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  std::unordered_map<uint32_t, int> pos; pos.reserve(ids.size() * 2);
+  for (size_t k = 0; k < ids.size(); ++k) pos[ids[k]] = (int)k;
+  struct Plan { int g = 0; double imbalance = 1e30; int max_classes = 1 << 30; std::vector<int> owner; };
+  Plan best;
+  const int g_max = (int)std::min<size_t>(ids.size(), (size_t)std::max(2, 2 * n_shards));
+  for (int g = 1; g <= g_max; ++g) {
+    const int nb = g * (g + 1) / 2;
+    auto block_of = [&](int a, int b) { if (a > b) std::swap(a, b); return a * g - a * (a - 1) / 2 + (b - a); };
+    std::vector<long> weight(nb, 0);
+    for (int k = 0; k < n_pairs; ++k) ++weight[block_of(pos[pairs[2 * k]] % g, pos[pairs[2 * k + 1]] % g)];
+    std::vector<int> order(nb);
+    for (int b = 0; b < nb; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+    std::vector<std::pair<int, int>> cls(nb);
+    for (int a = 0; a < g; ++a) for (int b = a; b < g; ++b) cls[block_of(a, b)] = {a, b};
+    std::vector<long> load(n_shards, 0);
+    std::vector<std::vector<char>> has(n_shards, std::vector<char>(g, 0));
+    Plan plan; plan.g = g; plan.owner.assign(nb, 0);
+    for (int b : order) {
+      if (weight[b] == 0) continue;
+      int pick = 0; long pl = -1; int padd = 0;
+      for (int r = 0; r < n_shards; ++r) {
+        const int add = (has[r][cls[b].first] ? 0 : 1) + ((cls[b].second != cls[b].first && !has[r][cls[b].second]) ? 1 : 0);
+        // least loaded first (2 % slack so that near-ties are decided by the views a shard already holds)
+        const bool better = pl < 0 || load[r] * 100 < pl * 98 || (load[r] * 98 <= pl * 100 && add < padd);
+        if (better) { pick = r; pl = load[r]; padd = add; }
+      }
+      plan.owner[b] = pick; load[pick] += weight[b];
+      has[pick][cls[b].first] = 1; has[pick][cls[b].second] = 1;
+    }
+    long mx = 0, sum = 0; int mc = 0;
+    for (int r = 0; r < n_shards; ++r) { mx = std::max(mx, load[r]); sum += load[r]; int cc = 0; for (char h : has[r]) cc += h; mc = std::max(mc, cc); }
+    plan.imbalance = (double)mx * n_shards / (double)std::max<long>(sum, 1) - 1.0;
+    plan.max_classes = mc;
+    // compare on the FRACTION of views a shard needs (max_classes / g), among acceptably balanced plans
+    auto frac = [](const Plan& p) { return (double)p.max_classes / p.g; };
+    const bool ok = plan.imbalance <= 0.03, best_ok = best.imbalance <= 0.03;
+    bool take;
+    if (best.g == 0) take = true;
+    else if (ok != best_ok) take = ok;
+    else if (ok) take = frac(plan) < frac(best) - 1e-9;
+    else take = plan.imbalance < best.imbalance - 1e-9;
+    if (take) best = plan;
+  }
+  const int g = best.g;
+  auto block_of = [&](int a, int b) { if (a > b) std::swap(a, b); return a * g - a * (a - 1) / 2 + (b - a); };
+  for (int k = 0; k < n_pairs; ++k) shard_of[k] = best.owner[block_of(pos[pairs[2 * k]] % g, pos[pairs[2 * k + 1]] % g)];
   return B200M_OK;
 }
 
@@ -1257,7 +1484,7 @@ int b200m_multi_match(b200m_multi* m, int n_views, const uint32_t* view_ids, con
     if (!index_of.count(pairs[p]))
       return fail(B200M_ERR_ARG, "pair references a view that was not given (RegionsPerView::getRegions would throw std::out_of_range)");
   std::vector<int32_t> shard_of(std::max(n_pairs, 1));
-  int rc = b200m_shard_pairs(pairs, n_pairs, nd, shard_of.data());
+  int rc = b200m_shard_pairs_2d(pairs, n_pairs, nd, shard_of.data());
   if (rc) return rc;
   struct Shard { std::vector<uint32_t> pairs; b200m_result* res = nullptr; int rc = B200M_OK; std::string err; };
   std::vector<Shard> sh(nd);

@@ -247,25 +247,32 @@ int b200io_load_matches_txt(const char* path, b200io_matches** out) {
   *out = nullptr;
   std::string txt;
   if (!read_all(path, txt)) return io_fail(B200IO_ERR_OPEN, std::string("can't open '") + path + "'");
-  std::unique_ptr<b200io_matches> res(new b200io_matches());
-  const char* p = txt.data(); const char* end = p + txt.size();
-  uint64_t I, J, nb;
-  while (next_u64(p, end, I) && next_u64(p, end, J) && next_u64(p, end, nb)) {     // `while (stream >> I >> J >> nbDescType)`, io.cpp:52
-    for (uint64_t d = 0; d < nb; ++d) {
-      std::string name; uint64_t cnt = 0;
-      if (!next_token(p, end, name) || !next_u64(p, end, cnt)) return io_fail(B200IO_ERR_FORMAT, "truncated descriptor-type header");
-      b200io_matches::Block b{(uint32_t)I, (uint32_t)J, name, (int64_t)res->data.size(), 0};
-      res->data.reserve(res->data.size() + cnt);
-      for (uint64_t e = 0; e < cnt; ++e) {
-        uint64_t a = 0, c = 0;
-        if (!next_u64(p, end, a) || !next_u64(p, end, c)) { a = c = 0; }              // failed extraction leaves IndMatch() (0, 0), like the stream code
-        res->data.push_back(b200m_match{(uint32_t)a, (uint32_t)c, 0.f, 0.f});
+  try {
+    std::unique_ptr<b200io_matches> res(new b200io_matches());
+    const char* p = txt.data(); const char* end = p + txt.size();
+    uint64_t I, J, nb;
+    while (next_u64(p, end, I) && next_u64(p, end, J) && next_u64(p, end, nb)) {     // `while (stream >> I >> J >> nbDescType)`, io.cpp:52
+      for (uint64_t d = 0; d < nb; ++d) {
+        std::string name; uint64_t cnt = 0;
+        if (!next_token(p, end, name) || !next_u64(p, end, cnt)) return io_fail(B200IO_ERR_FORMAT, "truncated descriptor-type header");
+        // a match needs at least 4 bytes ("0 0\n"): a count the rest of the file cannot hold is a corrupt / truncated file, not an
+        // allocation request (the reference's stream loop would push `cnt` default matches; behind a C ABI that must not be unbounded)
+        if (cnt > (uint64_t)(end - p) / 4 + 1) return io_fail(B200IO_ERR_FORMAT, "match count exceeds the remaining file size (truncated or corrupt matches file)");
+        b200io_matches::Block b{(uint32_t)I, (uint32_t)J, name, (int64_t)res->data.size(), 0};
+        res->data.reserve(res->data.size() + cnt);
+        for (uint64_t e = 0; e < cnt; ++e) {
+          uint64_t a = 0, c = 0;
+          if (!next_u64(p, end, a) || !next_u64(p, end, c)) return io_fail(B200IO_ERR_FORMAT, "truncated match list");
+          res->data.push_back(b200m_match{(uint32_t)a, (uint32_t)c, 0.f, 0.f});
+        }
+        b.end = (int64_t)res->data.size();
+        res->blocks.push_back(std::move(b));
       }
-      b.end = (int64_t)res->data.size();
-      res->blocks.push_back(std::move(b));
     }
+    *out = res.release();
+  } catch (const std::exception& e) {
+    return io_fail(B200IO_ERR_FORMAT, std::string("loading '") + path + "' failed: " + e.what());
   }
-  *out = res.release();
   return B200IO_OK;
 }
 

@@ -40,13 +40,15 @@ exact_top2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
   extern __shared__ float exsm[];
   float* Qs = exsm;
   float* Ds = exsm + EX_TQ * EX_LD;
-  const T* qraw = reinterpret_cast<const T*>(views[p.view_j].raw);
-  const T* draw = reinterpret_cast<const T*>(views[p.view_i].raw);
+  // T names the arithmetic (float: SSE order; uint8: exact integers - identical results whenever both apply); the element type of
+  // each view's buffer is its own storage type (integer-valued fp32 views are stored as u8)
+  const ViewDev& vq = views[p.view_j];
+  const ViewDev& vd = views[p.view_i];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
 
   for (int e = tid; e < EX_TQ * 128; e += 256) {
     const int r = e >> 7, c = e & 127;
-    Qs[r * EX_LD + c] = (q0 + r < (int)p.m_j) ? (float)qraw[(size_t)(q0 + r) * 128 + c] : 0.f;
+    Qs[r * EX_LD + c] = (q0 + r < (int)p.m_j) ? view_elem(vq, (size_t)(q0 + r) * 128 + c) : 0.f;
   }
   T2 best[4];
 #pragma unroll
@@ -56,7 +58,7 @@ exact_top2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
     __syncthreads();
     for (int e = tid; e < EX_TD * 128; e += 256) {
       const int r = e >> 7, c = e & 127;
-      Ds[r * EX_LD + c] = (d0 + r < (int)p.m_i) ? (float)draw[(size_t)(d0 + r) * 128 + c] : 0.f;
+      Ds[r * EX_LD + c] = (d0 + r < (int)p.m_i) ? view_elem(vd, (size_t)(d0 + r) * 128 + c) : 0.f;
     }
     __syncthreads();
     float acc[4][4][4];

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
-    "b200m_shard_pairs", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
+    "b200m_shard_pairs", "b200m_shard_pairs_2d", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
     "b200m_multi_last_gpu_ms", "b200m_guided_match", "b200m_guided_match_model",
 ]
 
@@ -249,6 +249,15 @@ def shard_pairs(pairs, n_shards: int) -> np.ndarray:
     return out[: p.shape[0]]
 
 
+def shard_pairs_2d(pairs, n_shards: int) -> np.ndarray:
+    """b200m_shard_pairs_2d: shard index of every pair with 2-D block sharding (a shard needs only part of the views). Host only."""
+    p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    out = np.zeros(max(p.shape[0], 1), np.int32)
+    _check(load_library().b200m_shard_pairs_2d(p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[0]), C.c_int(n_shards), out.ctypes.data_as(C.c_void_p)),
+           "b200m_shard_pairs_2d")
+    return out[: p.shape[0]]
+
+
 class MultiContext:
     """``b200m_multi``: one engine context per device, driven by one host thread each (single-process multi-GPU)."""
 
@@ -373,18 +382,62 @@ class ImageCollectionMatcherB200:
 
     def Match(self, regionsPerView: dict, pairs, map_PutativesMatches: dict | None = None) -> dict:
         """IImageCollectionMatcher::Match: appends {(I, J): matches} for every pair with a non-empty result
-        (ImageCollectionMatcher_generic.cpp:116-119: empty lists are not inserted; the output map is appended to)."""
-        out = {} if map_PutativesMatches is None else map_PutativesMatches
+        (ImageCollectionMatcher_generic.cpp:116-119: empty lists are not inserted; the output map is appended to).
+        Only the regions the pair list references are touched (the reference calls getRegions for those only, :55,:72).
+        Without an output map the result is a ``PairwiseMatches`` mapping (a dict view onto the engine's result arrays)."""
+        p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        used = set(np.unique(p).tolist())
+        needed = {v: r for v, r in regionsPerView.items() if v in used} if len(used) < len(regionsPerView) else regionsPerView
         if self.multi is not None:
-            pair_ids, offsets, matches = self._match_multi(regionsPerView, pairs)
+            pair_ids, offsets, matches = self._match_multi(needed, p)
         else:
-            self.upload(regionsPerView)
-            pair_ids, offsets, matches = self.match_uploaded(pairs, STAGE_FULL)
-        offs = offsets.tolist()
-        for (i, j), a, b in zip(pair_ids.tolist(), offs[:-1], offs[1:]):
-            if b > a:
-                out[(i, j)] = matches[a:b]     # view into the engine's result arena
-        return out
+            self.upload(needed)
+            pair_ids, offsets, matches = self.match_uploaded(p, STAGE_FULL)
+        res = PairwiseMatches(pair_ids, offsets, matches)
+        if map_PutativesMatches is None:
+            return res
+        map_PutativesMatches.update(res)
+        return map_PutativesMatches
+
+
+class PairwiseMatches(dict):
+    """{(I, J): matches[MATCH_DTYPE]} of one Match call for the pairs with a non-empty result, in PairSet order
+    (matching::PairwiseMatches, matching/IndMatch.hpp:148).  A dict whose entries are views into the engine's result arena;
+    the entries are materialised on first access, so a caller that only forwards the arrays (``pair_ids``, ``offsets``,
+    ``matches``: all pairs, CSR layout) pays nothing for the map."""
+
+    def __init__(self, pair_ids, offsets, matches):
+        super().__init__()
+        self.pair_ids, self.offsets, self.matches = pair_ids, offsets, matches
+        self._filled = False
+
+    def _fill(self):
+        if not self._filled:
+            self._filled = True
+            offs = self.offsets.tolist()
+            m = self.matches
+            for (i, j), a, b in zip(self.pair_ids.tolist(), offs[:-1], offs[1:]):
+                if b > a:
+                    dict.__setitem__(self, (i, j), m[a:b])
+        return self
+
+    def num_matches(self) -> int:
+        return int(self.offsets[-1]) if len(self.offsets) else 0
+
+
+def _lazy(name):
+    def f(self, *a, **k):
+        return getattr(dict, name)(self._fill(), *a, **k)
+    f.__name__ = name
+    return f
+
+
+for _n in ("__getitem__", "__contains__", "__iter__", "__len__", "__eq__", "__ne__", "__repr__", "keys", "values", "items", "get", "copy", "__bool__",
+           "pop", "__setitem__", "__delitem__", "setdefault", "update", "__reversed__", "__or__", "__ror__"):
+    if hasattr(dict, _n):
+        setattr(PairwiseMatches, _n, _lazy(_n))
+PairwiseMatches.__bool__ = lambda self: len(self) > 0
+PairwiseMatches.__hash__ = None
 
 
 MODEL_FUNDAMENTAL, MODEL_HOMOGRAPHY = 0, 1

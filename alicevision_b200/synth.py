@@ -85,6 +85,42 @@ def mldb_images(n_images: int, m: int, seed: int = SEED_DATA, shared: float = 0.
     return descs, xys
 
 
+class IndexedImages:
+    """Image k of a synthetic collection generated on its own (seeded by (seed, k)): a rank of a multi-GPU run builds only the
+    views its shard references, and every rank sees the same image k.  Same recipe as sift_images / mldb_images: a shared world
+    pool (planted correspondences, +-noise) plus fresh descriptors, general-position feature positions."""
+
+    def __init__(self, m: int, kind: str = "f32", seed: int = SEED_DATA, shared: float = 0.4, noise: int = 4, flip: float = 0.08, real: bool = False):
+        assert kind in ("f32", "u8", "bin")
+        self.m, self.kind, self.seed, self.shared, self.noise, self.flip, self.real = m, kind, seed, shared, noise, flip, real
+        rng = np.random.Generator(np.random.PCG64(seed))
+        if kind == "bin":
+            self.pool = rng.integers(0, 2, size=(max(2 * m, 8), 512), dtype=np.uint8)
+            self.pool[:, 486:] = 0
+        else:
+            self.pool = sift_pool(max(m, 8), rng)
+
+    def __call__(self, k: int):
+        rng = np.random.Generator(np.random.PCG64([self.seed, 0x5EED, int(k)]))
+        m = self.m
+        n_shared = min(int(m * (self.shared + rng.uniform(-0.1, 0.1))), m, self.pool.shape[0])
+        sel = rng.choice(self.pool.shape[0], size=n_shared, replace=False)
+        if self.kind == "bin":
+            a = self.pool[sel] ^ (rng.random((n_shared, 512)) < self.flip).astype(np.uint8)
+            a[:, 486:] = 0
+            b = rng.integers(0, 2, size=(m - n_shared, 512), dtype=np.uint8)
+            b[:, 486:] = 0
+            bits = np.concatenate([a, b], axis=0)[rng.permutation(m)]
+            return np.ascontiguousarray(np.packbits(bits, axis=1, bitorder="little")), positions(m, rng)
+        a = np.clip(self.pool[sel].astype(np.int16) + rng.integers(-self.noise, self.noise + 1, size=(n_shared, 128), dtype=np.int16), 0, 255)
+        b = sift_pool(m - n_shared, rng) if m > n_shared else np.zeros((0, 128), np.int16)
+        d = np.concatenate([a, np.clip(b, 0, 255)], axis=0)[rng.permutation(m)]
+        d = np.ascontiguousarray(d.astype(np.float32 if self.kind == "f32" else np.uint8))
+        if self.real and self.kind == "f32":
+            d = np.ascontiguousarray(d + rng.normal(0, 0.37, d.shape).astype(np.float32))
+        return d, positions(m, rng)
+
+
 def exhaustive_pairs(n: int) -> np.ndarray:
     """Upper-triangular pair list (matchingImageCollection/pairBuilder.cpp:22-46 with ids 0..n-1)."""
     i, j = np.triu_indices(n, 1)

@@ -134,6 +134,13 @@ int b200m_guided_match_model(b200m_ctx* ctx, uint32_t view_left, uint32_t view_r
  * the shards, direction alternating every round; all pairs of one database image stay together (its descriptors are
  * reused out of L2, ImageCollectionMatcher_generic.cpp:45-50 groups the same way).  Host-only, no GPU needed. */
 int b200m_shard_pairs(const uint32_t* pairs, int n_pairs, int n_shards, int32_t* shard_of);
+/* The sharding b200m_multi_match and bench.py use: 2-D blocks of the (symmetric) pair matrix, so that a shard needs only part of the
+ * views (8 shards: half of them, 4 shards: at most three quarters), which is what bounds the end-to-end rate once every shard has to
+ * stage its views through the same host.  View ids are dealt cyclically into g classes, the folded blocks {class(I), class(J)} are
+ * assigned heaviest-first to the least loaded shard; g is picked per call for balance (<= 3 %) then for the fewest views per shard.
+ * Pairs of one shard keep PairSet order, so all pairs of one database image stay adjacent (L2 reuse;
+ * ImageCollectionMatcher_generic.cpp:45-50 groups the same way).  Host-only. */
+int b200m_shard_pairs_2d(const uint32_t* pairs, int n_pairs, int n_shards, int32_t* shard_of);
 
 typedef struct b200m_multi b200m_multi;   /* one engine context per device + one host thread each */
 int b200m_multi_create(const int* devices, int n_devices, b200m_multi** out);

@@ -16,6 +16,7 @@ extern "C" int ref_guided_match(int dtype, int model, const void* desc_l, const 
 struct Mat3Lite { double v[9]; double operator()(int r, int c) const { return v[3 * r + c]; } };
 
 #include <cstdio>
+#include <memory>
 #include <random>
 
 using namespace aliceVision;
@@ -57,6 +58,27 @@ RegionsT* makeRegions(int n, unsigned seed, int lo, int hi, const RegionsT* plan
     }
     return r;
 }
+
+// Stand-in for the reference's ImageCollectionMatcher_generic (its .cpp needs FLANN / Boost, absent here) as the FALLBACK of the
+// collection adaptor: the same pair loop around the reference's own RegionsMatcher<ArrayMatcher_bruteForce> (forward pairs only).
+class RefLoopMatcher : public matchingImageCollection::IImageCollectionMatcher
+{
+  public:
+    mutable int calls = 0;
+    void Match(std::mt19937& rng, const RegionsPerView& rpv, const PairSet& pairs, EImageDescriberType descType, PairwiseMatches& out) const override
+    {
+        ++calls;
+        for (const Pair& p : pairs)
+        {
+            const Regions& ri = rpv.getRegions(p.first, descType);
+            const Regions& rj = rpv.getRegions(p.second, descType);
+            if (ri.RegionCount() == 0 || rj.RegionCount() == 0) continue;
+            RegionsMatcher<ArrayMatcher_bruteForce<unsigned char, L2_Vectorized<unsigned char>>> fw(rng, ri, true);
+            IndMatches v; fw.Match(0.8f, rj, v);
+            if (!v.empty()) out[p].emplace(descType, v);
+        }
+    }
+};
 
 int main()
 {
@@ -174,6 +196,37 @@ int main()
             for (size_t k = 0; k < std::min(w.size(), g.size()); ++k)
                 CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j && w[k]._distanceRatio == g[k]._distanceRatio && w[k]._distance == g[k]._distance);
         }
+    }
+    // --- error convention: an engine that cannot be created, or that fails in Match, delegates to the fallback matcher
+    //     (the integration passes ImageCollectionMatcher_generic) instead of aborting featureMatching; without a fallback it throws
+    {
+        auto fb = std::make_shared<RefLoopMatcher>();
+        matchingImageCollection::ImageCollectionMatcher_b200 broken(0.8f, false, false, /*device=*/99, fb);   // no such device
+        CHECK(broken.usesFallbackOnly());
+        PairwiseMatches got, want;
+        broken.Match(rng, rpv, pairs, EImageDescriberType::SIFT, got);
+        RefLoopMatcher().Match(rng, rpv, pairs, EImageDescriberType::SIFT, want);
+        CHECK(fb->calls == 1 && got.size() == want.size() && !want.empty());
+        for (auto& kv : want)
+        {
+            auto it = got.find(kv.first);
+            CHECK(it != got.end());
+            if (it == got.end()) continue;
+            const IndMatches& w = kv.second.at(EImageDescriberType::SIFT);
+            const IndMatches& g = it->second.at(EImageDescriberType::SIFT);
+            CHECK(w.size() == g.size());
+            for (size_t k = 0; k < std::min(w.size(), g.size()); ++k) CHECK(w[k]._i == g[k]._i && w[k]._j == g[k]._j);
+        }
+        bool threw = false;
+        try { matchingImageCollection::ImageCollectionMatcher_b200 nofb(0.8f, false, false, /*device=*/99); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw);
+        // a working engine never touches the fallback, and gives the same lists
+        auto fb2 = std::make_shared<RefLoopMatcher>();
+        matchingImageCollection::ImageCollectionMatcher_b200 ok(0.8f, false, false, 0, fb2);
+        PairwiseMatches got2;
+        ok.Match(rng, rpv, pairs, EImageDescriberType::SIFT, got2);
+        CHECK(!ok.usesFallbackOnly() && fb2->calls == 0 && got2.size() == want.size());
+        std::printf("fallback matcher: %zu pairs through the fallback, engine path untouched by it\n", want.size());
     }
     // --- IRegionsMatcher adaptor (what createRegionsMatcher returns for the new enum values) vs the reference's
     //     RegionsMatcher<ArrayMatcher_bruteForce<...>>: one database, several queries, uchar / float / binary, factory rules

@@ -490,3 +490,81 @@ def test_other_descriptor_lengths_on_the_collection_surface(kind):
     ok_w, want1 = P.regions_match(descs[0], xys[0], descs[1], xys[1], 0.8, False)
     assert ok == ok_w
     assert_same({0: got1}, {0: want1})
+
+
+# ---------------------------------------------------------------------------------------------- round 2: staging / finishing variants
+def _fresh_matcher(env: dict, hamming=False, cross=False):
+    """An ImageCollectionMatcherB200 on its OWN engine context created under `env` (the context reads its switches at creation)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ctx = matching.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    t = EMatcherType.BRUTE_FORCE_HAMMING_B200 if hamming else EMatcherType.BRUTE_FORCE_L2_B200
+    return ImageCollectionMatcherB200(0.8, cross, t, ctx)
+
+
+@pytest.mark.parametrize("kind", ["f32", "u8", "bin", "adv"])
+def test_device_finishing_equals_host_finishing(ora, kind):
+    """The finishing stage on the device (finish.cuh: general-position views) and the literal host stage give the reference's lists;
+    views with colliding coordinates are left to the host by the device stage (flag from pos_rank_kernel)."""
+    hamming = kind == "bin"
+    if hamming:
+        descs, xys = synth.mldb_images(4, 1100, seed=131)
+    else:
+        descs, xys = synth.sift_images(4, 1100, np.float32 if kind == "f32" else np.uint8, seed=131, pool_factor=1.0, generic_positions=kind != "adv")
+    if kind == "f32":                 # one view in general position, one not, inside the same batch
+        xys[2] = synth.positions(1100, np.random.default_rng(3), generic=False)
+    cut = [1100, 901, 1100, 257]
+    descs = [d[:c] for d, c in zip(descs, cut)]; xys = [x[:c] for x, c in zip(xys, cut)]
+    pairs = [(0, 1), (1, 0), (2, 3), (3, 2), (0, 2), (2, 0), (1, 1)]
+    views = {i: (descs[i], xys[i]) for i in range(4)}
+    for cross in (False, True):
+        want = ora.collection_match(descs, xys, pairs, 0.8, cross, hamming)
+        for env in ({"B200M_DEVICE_FINISH": "1"}, {"B200M_DEVICE_FINISH": "0"}):
+            m = _fresh_matcher(env, hamming, cross)
+            assert_same(dict(m.Match(views, pairs)), want)
+            m.ctx.close()
+
+
+def test_u8_staging_of_integer_valued_fp32(ora):
+    """Integer-valued fp32 descriptors are staged and stored as uchar (hostconv.hpp); with the staging switched off, and for a view
+    whose first rows look integer but a later value is not (the probe passes, the checked conversion of a later chunk fails and the
+    view is re-uploaded as fp32), the results are the reference's."""
+    descs, xys = synth.sift_images(4, 1300, np.float32, seed=141, pool_factor=1.0)
+    descs[2] = descs[2].copy(); descs[2][777, 5] += 0.25            # surprise far behind the probe
+    descs[3] = synth.real_valued([descs[3]])[0]                      # real-valued from the first row
+    pairs = [(0, 1), (1, 0), (0, 2), (2, 0), (0, 3), (3, 1), (2, 3)]
+    views = {i: (descs[i], xys[i]) for i in range(4)}
+    want = ora.collection_match(descs, xys, pairs, 0.8)
+    for env in ({"B200M_U8_STAGING": "1"}, {"B200M_U8_STAGING": "0"}, {"B200M_U8_STAGING": "1", "B200M_UP_CHUNK_MB": "1"}):
+        m = _fresh_matcher(env)
+        got = dict(m.Match(views, pairs))
+        assert_same(got, want)
+        assert m.ctx.last_tc_pairs() == 2 and m.ctx.exactness_errors() == 0     # (0,1), (1,0): both views integer-valued
+        m.ctx.close()
+    # guided matching between an integer-valued (stored as uchar) and a real-valued fp32 view: temporary fp32 expansion
+    from alicevision_b200 import Regions, matching as mt
+    F = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float64)
+    got = mt.guidedMatching(F, Regions(descs[0], xys[0]), Regions(descs[3], xys[3]), 400.0, 0.81)
+    want_g = ora.guided_match(descs[0], xys[0], descs[3], xys[3], F, 400.0, 0.81)
+    assert np.array_equal(got["i"], want_g["i"]) and np.array_equal(got["j"], want_g["j"]) and len(got) > 0
+
+
+def test_upload_rejects_duplicate_ids_and_survives():
+    descs, xys = synth.sift_images(2, 300, np.uint8, seed=151, pool_factor=1.0)
+    m = ImageCollectionMatcherB200()
+    m.clear()
+    import ctypes as C
+    lib = m.ctx.lib
+    ids = np.array([4, 4], np.uint32); counts = np.array([300, 300], np.int32)
+    dptr = (C.c_void_p * 2)(descs[0].ctypes.data, descs[1].ctypes.data)
+    rc = lib.b200m_upload_views_async(m.ctx._h, C.c_int(2), ids.ctypes.data_as(C.c_void_p), dptr, counts.ctypes.data_as(C.c_void_p), C.c_int(128), C.c_int(1), None)
+    assert rc == 1 and b"twice" in lib.b200m_last_error()
+    m.upload({0: (descs[0], xys[0]), 1: (descs[1], xys[1])})      # the context is still usable
+    assert len(m.Match({}, [(0, 1)])) == 1

@@ -179,3 +179,19 @@ def test_golden_files_written_by_the_reference():
             rio.saveFeatsToFile(os.path.join(t, "a.feat"), f); rio.saveDescsToBinFile(os.path.join(t, "a.desc"), d)
             assert open(os.path.join(t, "a.feat"), "rb").read() == open(fp, "rb").read()
             assert open(os.path.join(t, "a.desc"), "rb").read() == open(dp, "rb").read()
+
+
+def test_corrupt_matches_file_is_an_error_not_an_allocation(tmp_path):
+    """A count the file cannot hold (corrupt / truncated matches.txt) is reported as a format error: the C ABI never throws and
+    never tries to allocate or emit `count` default matches."""
+    bad = tmp_path / "bad.txt"
+    bad.write_text("0 1\n1\nsift 4000000000000\n1 2\n")
+    import pytest
+    out = {}
+    with pytest.raises(IOError, match="match count exceeds"):
+        rio.LoadMatchFile(out, str(bad))
+    assert out == {}
+    cut = tmp_path / "cut.txt"
+    cut.write_text("0 1\n1\nsift 3\n1 2\n3 4\n")           # announces 3 matches, holds 2
+    with pytest.raises(IOError, match="truncated"):
+        rio.LoadMatchFile({}, str(cut))

@@ -18,7 +18,7 @@ def _worker(rank, world, port, n_img, q):
     from alicevision_b200 import synth
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     pairs = synth.exhaustive_pairs(n_img)
-    mine = bench.shard_pairs(pairs, rank, world)
+    mine = bench.shard_pairs(pairs, rank, world, "rows")
     # what bench.py reduces: max of per-rank times, sum of per-rank pair counts
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     n = torch.tensor([float(len(mine))], dtype=torch.float64)
@@ -57,7 +57,7 @@ def test_shard_sizes_weak_scaling_table():
     from alicevision_b200 import synth
     for world, n_img in bench.IMAGES_FOR_GPUS.items():
         pairs = synth.exhaustive_pairs(n_img)
-        sizes = [len(bench.shard_pairs(pairs, r, world)) for r in range(world)]
+        sizes = [len(bench.shard_pairs(pairs, r, world, "rows")) for r in range(world)]
         assert sum(sizes) == len(pairs)
         assert max(sizes) - min(sizes) <= n_img
         assert abs(np.mean(sizes) - 4950) / 4950 < 0.02
@@ -83,3 +83,36 @@ def test_c_sharding_properties():
     sizes = np.bincount(s, minlength=8)
     assert sizes.sum() == len(vt) and sizes.max() < 1.35 * sizes.mean()
     assert len(matching.shard_pairs(np.zeros((0, 2), np.uint32), 4)) == 0
+
+
+def test_2d_block_sharding_properties():
+    """b200m_shard_pairs_2d (what bench.py and b200m_multi_match use): disjoint cover, balanced, and a shard needs only part of
+    the views - half of them at 8 shards, at most three quarters at 4 - where sharding by database image needs nearly all."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from alicevision_b200 import matching, synth
+    for world, n_img in bench.IMAGES_FOR_GPUS.items():
+        pairs = synth.exhaustive_pairs(n_img)
+        s = matching.shard_pairs_2d(pairs, world)
+        assert s.min() >= 0 and s.max() < world and len(s) == len(pairs)
+        sizes = np.bincount(s, minlength=world)
+        assert sizes.sum() == len(pairs) and sizes.max() <= 1.03 * sizes.mean()
+        assert abs(sizes.mean() - 4950) / 4950 < 0.02
+        views = [len(np.unique(pairs[s == r])) for r in range(world)]
+        limit = {1: 1.0, 2: 1.0, 4: 0.76, 8: 0.51}[world]
+        assert max(views) <= limit * n_img + 1, (world, views)
+        mine = [bench.shard_pairs(pairs, r, world, "2d") for r in range(world)]
+        assert sum(len(m) for m in mine) == len(pairs)
+        for m in mine:                                   # PairSet order inside a shard: the pairs of one database image stay adjacent
+            assert m.tolist() == sorted(m.tolist())
+    vt = synth.voctree_like_pairs(1000, k=50)            # BASELINE configs[2]
+    for world, frac in ((4, 0.76), (8, 0.51)):
+        s = matching.shard_pairs_2d(vt, world)
+        sizes = np.bincount(s, minlength=world)
+        assert sizes.sum() == len(vt) and sizes.max() <= 1.03 * sizes.mean()
+        assert max(len(np.unique(vt[s == r])) for r in range(world)) <= frac * 1000 + 1
+    # degenerate inputs: more shards than images, one pair, no pair
+    assert matching.shard_pairs_2d(np.array([[3, 9]], np.uint32), 8).tolist()[0] in range(8)
+    assert len(matching.shard_pairs_2d(np.zeros((0, 2), np.uint32), 4)) == 0
+    s = matching.shard_pairs_2d(synth.exhaustive_pairs(5), 8)
+    assert len(s) == 10 and s.min() >= 0 and s.max() < 8
