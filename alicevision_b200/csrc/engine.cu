@@ -174,6 +174,7 @@ struct ViewHost {
   uint32_t id = 0;
   int m = 0, dim = 0, dtype = 0, m_pad = 0;
   void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr;
+  __half* augq16 = nullptr; float* err = nullptr; uint32_t* stats = nullptr;   // real-valued tensor-core path (prep.cuh): query-side limbs, rounding-error bounds
   bool stored_u8 = false;     // dtype == DT_F32 whose values are integers in 0..255: staged and kept on the device as uchar (hostconv.hpp)
   float* d_xy = nullptr; uint32_t* d_yrank = nullptr;   // positions + rank of y on the device (device finishing stage, finish.cuh)
   bool failed = false;        // its upload job failed: the device buffers were never filled
@@ -188,6 +189,8 @@ struct ViewHost {
   int store_dtype() const { return stored_u8 ? (int)DT_U8 : dtype; }
   bool tc_capable() const { return dtype != DT_BIN && dim == 128 && m > 0; }
   bool tc_ok() const { return tc_capable() && (flags & VF_EXACT_MASK) == 0; }
+  // real-valued rows may take the tensor-core FILTER path (MODE_REAL): fp16 range and the half-norm limbs must hold, integers need not
+  bool real_ok() const { return tc_capable() && (flags & (VF_RANGE | VF_NORM)) == 0 && m <= REAL_MAX_ROWS; }
 };
 
 struct UploadJob {
@@ -200,23 +203,34 @@ struct BatchBuf {
   PairDev* d_pairs = nullptr; WorkItem* d_items = nullptr; Cand* d_cands = nullptr; int* d_count = nullptr; int* d_off = nullptr;
   Rec* d_out = nullptr;
   FinMatch* d_fin = nullptr; int* d_fin_count = nullptr; uint32_t* d_scratch = nullptr;   // device finishing stage (finish.cuh)
+  WorkItem* d_items_real = nullptr; WorkItem* h_items_real = nullptr;                     // work items of the real-valued pairs (own launch)
+  uint32_t* d_candx = nullptr; uint2* d_fb = nullptr; int* d_fb_count = nullptr;          // real-valued path: 5th candidate word, fallback list (pair, query)
   PairDev* h_pairs = nullptr; WorkItem* h_items = nullptr; int* h_meta = nullptr; Rec* h_out = nullptr;   // pinned
-  cudaEvent_t ev_meta = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev_meta = nullptr, ev_copy = nullptr, ev_tab = nullptr;
 };
 
 constexpr int PAIR_CAP = 4096;            // directed pairs per batch
 constexpr long CAND_CAP = 4l << 20;       // candidate slots per batch (sum of m_j)
 constexpr long ITEM_CAP = CAND_CAP / 64 + PAIR_CAP;
 constexpr long SLOT_CAP = 8l << 20;       // database rows per batch (sum of m_i): scratch of the device finishing stage
-constexpr int META_INTS = 3 * PAIR_CAP + 2;   // pinned per-batch read-back: counts | offsets (+1) | finishing counts
+constexpr int META_INTS = 3 * PAIR_CAP + 3;   // pinned per-batch read-back: counts | offsets (+1) | finishing counts | fallback rows of the real-valued path
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// grow-only device scratch of b200m_knn (Surface 1)
+struct KnnScratch {
+  int cap = 0; size_t raw_bytes = 0;
+  void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr; __half* augq16 = nullptr; float* err = nullptr;
+  Cand* cands = nullptr; int32_t* idx = nullptr; uint32_t* dist = nullptr; WorkItem* items = nullptr; uint8_t* small = nullptr;
+};
+
 struct b200m_ctx {
   int device = 0, num_sms = 148;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, up_stream = nullptr;
+  KnnScratch knn;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, up_stream = nullptr, tab_stream = nullptr, pack_stream = nullptr;
+  bool pipe_streams = true;       // tables / packing+finishing on their own streams (B200M_PIPE_STREAMS=0: everything on the search stream)
   bool own_stream = false;
   EncodeTiledFn encode = nullptr;
   std::deque<ViewHost> views;     // deque: references stay valid while pool tasks (position checks) run
@@ -250,14 +264,17 @@ struct b200m_ctx {
   bool device_finish = true;      // finishing stage on the device for views in general position (B200M_DEVICE_FINISH=0 disables)
   std::shared_ptr<Recycler> recycler = std::make_shared<Recycler>();
   bool force_exact = false;
+  bool real_tc = true;            // real-valued fp32 pairs on the tensor-core filter kernel (B200M_REAL_TC=0: exact CUDA-core kernel as in round 1)
+  long real_fused_rows = 6144;    // average database rows per item from which the real-valued re-scoring runs inside the filter kernel
   int tc_variant = 4;             // 1 = single-CTA kernel (l2_tc.cuh); CTA-pair kernel (l2_tc2.cuh): 2 = 8 epilogue warps, 3 = 16 epilogue warps,
                                   // 4 (default) = 8 epilogue warps + half-norms folded into the GEMM (AUG)
   // last-call instrumentation
   double last_gpu_ms = 0, last_search_ms = 0; int last_launches = 0, last_tc_pairs = 0; int64_t last_records = 0;
+  int last_real_pairs = 0; int64_t last_fallback_rows = 0;      // real-valued pairs on the tensor-core filter kernel; queries left to the exact_rows fallback
   unsigned err_total = 0;
 };
 
-struct b200m_db { b200m_ctx* ctx; ViewHost v; int metric; };
+struct b200m_db { b200m_ctx* ctx; ViewHost v; int metric; ViewDev dev; };
 
 struct b200m_result {
   std::vector<uint32_t> pair_ids; std::vector<int64_t> offsets;
@@ -282,6 +299,9 @@ static int alloc_view_buffers(b200m_ctx* c, ViewHost& v) {
     CK(cudaMallocAsync((void**)&v.nbh, (size_t)v.m_pad * 4, c->stream));
     CK(cudaMallocAsync((void**)&v.nrm, (size_t)v.m_pad * 4, c->stream));
     CK(cudaMallocAsync((void**)&v.aug16, (size_t)v.m_pad * 32, c->stream));
+    CK(cudaMallocAsync((void**)&v.augq16, (size_t)v.m_pad * 32, c->stream));
+    CK(cudaMallocAsync((void**)&v.err, (size_t)v.m_pad * 4, c->stream));
+    CK(cudaMallocAsync((void**)&v.stats, 16, c->stream));
   }
   return B200M_OK;
 }
@@ -291,15 +311,19 @@ static void free_view_buffers(b200m_ctx* c, ViewHost& v) {
   if (v.nbh) cudaFreeAsync(v.nbh, c->stream);
   if (v.nrm) cudaFreeAsync(v.nrm, c->stream);
   if (v.aug16) cudaFreeAsync(v.aug16, c->stream);
+  if (v.augq16) cudaFreeAsync(v.augq16, c->stream);
+  if (v.err) cudaFreeAsync(v.err, c->stream);
+  if (v.stats) cudaFreeAsync(v.stats, c->stream);
   if (v.d_xy) cudaFreeAsync(v.d_xy, c->stream);
   if (v.d_yrank) cudaFreeAsync(v.d_yrank, c->stream);
   v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr; v.aug16 = nullptr; v.d_xy = nullptr; v.d_yrank = nullptr;
+  v.augq16 = nullptr; v.err = nullptr; v.stats = nullptr;
 }
 
 static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   std::memset(&d, 0, sizeof(d));
   d.raw = v.raw; d.h16 = v.h16; d.nbh = v.nbh; d.nrm = v.nrm; d.aug16 = v.aug16; d.m = v.m; d.dim = v.dim; d.dtype = v.store_dtype();
-  d.yrank = v.d_yrank;
+  d.yrank = v.d_yrank; d.augq16 = v.augq16; d.err = v.err; d.stats = v.stats;
   if (v.tc_capable()) {
     const cuuint64_t gdim[2] = {128, (cuuint64_t)v.m};
     const cuuint64_t gstr[1] = {256};
@@ -318,6 +342,9 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
       CUresult r = c->encode(&d.tmap_aug, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.aug16, adim, astr, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled(aug) failed: " + std::to_string((int)r));
+      r = c->encode(&d.tmap_augq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)v.augq16, adim, astr, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(B200M_ERR_CUDA, "cuTensorMapEncodeTiled(augq) failed: " + std::to_string((int)r));
     }
   }
   return B200M_OK;
@@ -327,8 +354,9 @@ static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag, cudaStrea
   (void)c;
   if (!v.tc_capable()) return B200M_OK;
   const int grid = (v.m_pad + 7) / 8;
-  if (v.store_dtype() == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
-  else prep_view_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16);
+  CK(cudaMemsetAsync(v.stats, 0, 16, st));
+  if (v.store_dtype() == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16, v.augq16, v.err, v.stats);
+  else prep_view_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16, v.augq16, v.err, v.stats);
   CK(cudaGetLastError());
   return B200M_OK;
 }
@@ -385,17 +413,25 @@ static int ensure_batch_buffers(b200m_ctx* c) {
     CK(cudaMalloc((void**)&b.d_fin, sizeof(FinMatch) * CAND_CAP));
     CK(cudaMalloc((void**)&b.d_fin_count, sizeof(int) * PAIR_CAP));
     CK(cudaMalloc((void**)&b.d_scratch, sizeof(uint32_t) * 2 * SLOT_CAP));
+    CK(cudaMalloc((void**)&b.d_items_real, sizeof(WorkItem) * ITEM_CAP));
+    CK(cudaMalloc((void**)&b.d_candx, sizeof(uint32_t) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_fb, sizeof(uint2) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_fb_count, sizeof(int)));
+    CK(cudaMallocHost((void**)&b.h_items_real, sizeof(WorkItem) * ITEM_CAP));
     CK(cudaMallocHost((void**)&b.h_pairs, sizeof(PairDev) * PAIR_CAP));
     CK(cudaMallocHost((void**)&b.h_items, sizeof(WorkItem) * ITEM_CAP));
     CK(cudaMallocHost((void**)&b.h_meta, sizeof(int) * META_INTS));
     CK(cudaMallocHost((void**)&b.h_out, sizeof(Rec) * CAND_CAP));
     CK(cudaEventCreateWithFlags(&b.ev_meta, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b.ev_tab, cudaEventDisableTiming));
   }
   CK(cudaFuncSetAttribute(tc::l2_top2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<false>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<false>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true, true>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
@@ -493,6 +529,9 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->tab_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("B200M_PIPE_STREAMS")) c->pipe_streams = atoi(e) != 0;
   CK(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -513,6 +552,8 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   c->pool.reset(new Pool(std::min(std::max(ht, 1), 32), c->cpus));
   if (const char* e = getenv("B200M_U8_STAGING")) c->u8_staging = atoi(e) != 0;
   if (const char* e = getenv("B200M_DEVICE_FINISH")) c->device_finish = atoi(e) != 0;
+  if (const char* e = getenv("B200M_REAL_TC")) c->real_tc = atoi(e) != 0;
+  if (const char* e = getenv("B200M_REAL_FUSED_ROWS")) c->real_fused_rows = std::max(0l, atol(e));
   *out = c.release();
   return B200M_OK;
 }
@@ -536,9 +577,11 @@ void b200m_ctx_destroy(b200m_ctx* c) {
     BatchBuf& b = c->buf[s];
     cudaFree(b.d_pairs); cudaFree(b.d_items); cudaFree(b.d_cands); cudaFree(b.d_count); cudaFree(b.d_off); cudaFree(b.d_out);
     cudaFree(b.d_fin); cudaFree(b.d_fin_count); cudaFree(b.d_scratch);
+    cudaFree(b.d_items_real); cudaFree(b.d_candx); cudaFree(b.d_fb); cudaFree(b.d_fb_count); cudaFreeHost(b.h_items_real);
     cudaFreeHost(b.h_pairs); cudaFreeHost(b.h_items); cudaFreeHost(b.h_meta); cudaFreeHost(b.h_out);
     if (b.ev_meta) cudaEventDestroy(b.ev_meta);
     if (b.ev_copy) cudaEventDestroy(b.ev_copy);
+    if (b.ev_tab) cudaEventDestroy(b.ev_tab);
   }
   for (auto& e : c->tev) cudaEventDestroy(e);
   for (int k = 0; k < b200m_ctx::NSTG; ++k) { if (c->stg[k]) cudaFreeHost(c->stg[k]); if (c->stg_ev[k]) cudaEventDestroy(c->stg_ev[k]); }
@@ -547,8 +590,13 @@ void b200m_ctx_destroy(b200m_ctx* c) {
   for (auto& e : c->view_ev) if (e) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_alloc);
   cudaStreamDestroy(c->up_stream);
+  cudaStreamDestroy(c->tab_stream); cudaStreamDestroy(c->pack_stream);
   if (c->d_trace) cudaFree(c->d_trace);
   cudaFree(c->d_views); cudaFree(c->d_flags); cudaFree(c->d_err);
+  {
+    KnnScratch& k = c->knn;
+    for (void* q : {(void*)k.raw, (void*)k.h16, (void*)k.nbh, (void*)k.nrm, (void*)k.aug16, (void*)k.augq16, (void*)k.err, (void*)k.cands, (void*)k.idx, (void*)k.dist, (void*)k.items, (void*)k.small}) if (q) cudaFree(q);
+  }
   cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
   cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -632,6 +680,7 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     if (!c->stg_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_ev[k], cudaEventDisableTiming));
   }
   std::vector<int>& bad = *job.bad;
+  double t_ring = 0, t_task = 0, t_fin = 0;                // B200M_TIMING: where the issuing thread waits
   auto finish_view = [&](int i) -> int {                   // runs right after the last chunk of view i was enqueued
     const int slot = job.slots[i];
     ViewHost& v = c->views[slot];
@@ -655,7 +704,8 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
       if (rc) return rc;
     }
     if (v.d_xy) {
-      pos_rank_kernel<<<(v.m + PR_THREADS - 1) / PR_THREADS, PR_THREADS, 0, c->up_stream>>>((const float2*)v.d_xy, v.m, v.d_yrank, c->d_flags + slot);
+      CK(cudaMemsetAsync(v.d_yrank, 0, (size_t)v.m * 4, c->up_stream));
+      pos_rank_kernel<<<dim3((v.m + PR_THREADS - 1) / PR_THREADS, (v.m + PR_KRANGE - 1) / PR_KRANGE), PR_THREADS, 0, c->up_stream>>>((const float2*)v.d_xy, v.m, v.d_yrank, c->d_flags + slot);
       CK(cudaGetLastError());
     }
     if (flagged) CK(cudaMemcpyAsync(c->h_flags + slot, c->d_flags + slot, 4, cudaMemcpyDeviceToHost, c->up_stream));
@@ -673,20 +723,24 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
   auto issue_h2d = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
     const int sidx = (int)(k % b200m_ctx::NSTG);
+    const double tw0 = timing ? now() : 0;
     grp[k]->wait();
+    if (timing) t_task += now() - tw0;
     const ViewHost& v = c->views[job.slots[ch.view]];
     if (ch.bytes && !(ch.kind == CK_U8 && __atomic_load_n(&bad[ch.view], __ATOMIC_ACQUIRE))) {
       char* dst = ch.kind == CK_XY ? (char*)v.d_xy : (char*)v.raw;
       CK(cudaMemcpyAsync(dst + ch.off, c->stg[sidx], ch.bytes, cudaMemcpyHostToDevice, c->up_stream));
       CK(cudaEventRecord(c->stg_ev[sidx], c->up_stream));
     }
-    if (ch.last) return finish_view(ch.view);
+    if (ch.last) { const double tf0 = timing ? now() : 0; const int rc = finish_view(ch.view); if (timing) t_fin += now() - tf0; return rc; }
     return B200M_OK;
   };
   for (size_t k = 0; k < chunks.size(); ++k) {
     const Chunk& ch = chunks[k];
     const int sidx = (int)(k % b200m_ctx::NSTG);
+    const double tr0 = timing ? now() : 0;
     CK(cudaEventSynchronize(c->stg_ev[sidx]));             // the H2D that last used this staging buffer is done (no-op when never recorded)
+    if (timing) t_ring += now() - tr0;
     grp[k].reset(new TaskGroup());
     if (ch.bytes) {
       char* d = (char*)c->stg[sidx]; TaskGroup* g = grp[k].get();
@@ -711,7 +765,7 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
     if (k >= (size_t)LAG) { int rc = issue_h2d(k - LAG); if (rc) return rc; }
   }
   for (size_t k = chunks.size() >= (size_t)LAG ? chunks.size() - LAG : 0; k < chunks.size(); ++k) { int rc = issue_h2d(k); if (rc) return rc; }
-  if (timing) { const double t_end = now(); CK(cudaStreamSynchronize(c->up_stream)); fprintf(stderr, "[b200m] upload job n=%d: copies issued in %.2f ms, drain %.2f ms\n", job.n_views, t_end - t_begin, now() - t_end); }
+  if (timing) { const double t_end = now(); CK(cudaStreamSynchronize(c->up_stream)); fprintf(stderr, "[b200m] upload job n=%d (%zu chunks): copies issued in %.2f ms (waiting: ring %.2f, staging tasks %.2f; per-view finish calls %.2f), drain %.2f ms\n", job.n_views, chunks.size(), t_end - t_begin, t_ring, t_task, t_fin, now() - t_end); }
   return B200M_OK;
 }
 
@@ -1012,13 +1066,15 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   size_t tev_used = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
   int launches = 0;
-  int64_t total_records = 0;
+  int64_t total_records = 0, fallback_rows = 0;
+  int real_pairs = 0;
+  const bool real_tc = !c->force_exact && c->real_tc && c->tc_variant == 4;
 
   auto enqueue = [&](size_t bi) -> int {
     const Batch& B = batches[bi];
     BatchBuf& bb = c->buf[bi & 1];
     const int np = (int)(B.end - B.begin);
-    uint32_t cbase = 0, sbase = 0; int n_items = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
+    uint32_t cbase = 0, sbase = 0; int n_items = 0, n_items_real = 0; int max_qblk_exact = 0, max_qblk_ham = 0;
     // In-kernel exactness pass only when a work item lasts long enough (>= 24 database tiles on average) for two warps to
     // re-score the previous item's candidates behind it; shorter images use the stand-alone exactness kernel.
     // the views of this batch must be complete on the device; their exactness flags decide tensor-core vs exact kernel
@@ -1030,12 +1086,18 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       if (d.mode == PM_TC) {
         const ViewHost& vi = c->views[d.slot_i]; const ViewHost& vj = c->views[d.slot_j];
         if (!c->force_exact && vi.tc_ok() && vj.tc_ok()) ++tc_pairs;
+        else if (real_tc && vi.real_ok() && vj.real_ok()) { d.mode = PM_TC_REAL; ++real_pairs; }   // real-valued fp32: tensor-core filter + exact re-scoring
         else d.mode = vi.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8;
       }
     }
-    long tc_rows = 0, tc_n = 0;
-    for (int p = 0; p < np; ++p) if (dir[seqv[B.begin + p]].mode == PM_TC) { tc_rows += c->views[dir[seqv[B.begin + p]].slot_i].m; ++tc_n; }
+    long tc_rows = 0, tc_n = 0, real_rows = 0, real_n = 0;
+    for (int p = 0; p < np; ++p) {
+      const Directed& d = dir[seqv[B.begin + p]];
+      if (d.mode == PM_TC) { tc_rows += c->views[d.slot_i].m; ++tc_n; }
+      if (d.mode == PM_TC_REAL) { real_rows += c->views[d.slot_i].m; ++real_n; }
+    }
     const bool fused = c->tc_variant >= 2 && tc_n > 0 && tc_rows / tc_n >= 6144;
+    const bool fused_real = real_n > 0 && real_rows / real_n >= c->real_fused_rows;
     bool any_f32 = false, any_u8 = false, any_ham = false, any_gf32 = false, any_gu8 = false; int max_qblk_gen = 0;
     for (int p = 0; p < np; ++p) {
       const Directed& d = dir[seqv[B.begin + p]];
@@ -1046,28 +1108,50 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       cbase += (uint32_t)vj.m; sbase += (uint32_t)vi.m;
       const int qrows = c->tc_variant >= 2 ? 2 * tc2::BM : tc::BM;   // queries per work item
       if (d.mode == PM_TC) for (int qt = 0; qt < (vj.m + qrows - 1) / qrows; ++qt) bb.h_items[n_items++] = WorkItem{(uint32_t)p, (uint32_t)qt};
+      if (d.mode == PM_TC_REAL) for (int qt = 0; qt < (vj.m + 2 * tc2::BM - 1) / (2 * tc2::BM); ++qt) bb.h_items_real[n_items_real++] = WorkItem{(uint32_t)p, (uint32_t)qt};
       if (d.mode == PM_EXACT_F32) { any_f32 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_EXACT_U8) { any_u8 = true; max_qblk_exact = std::max(max_qblk_exact, (vj.m + EX_TQ - 1) / EX_TQ); }
       if (d.mode == PM_HAMMING) { any_ham = true; max_qblk_ham = std::max(max_qblk_ham, (vj.m + HM_TQ - 1) / HM_TQ); }
       if (d.mode == PM_GENERIC_F32 || d.mode == PM_GENERIC_U8) { (d.mode == PM_GENERIC_F32 ? any_gf32 : any_gu8) = true; max_qblk_gen = std::max(max_qblk_gen, (vj.m + 3) / 4); }
     }
-    CK(cudaMemcpyAsync(bb.d_pairs, bb.h_pairs, sizeof(PairDev) * np, cudaMemcpyHostToDevice, c->stream));
-    if (n_items) CK(cudaMemcpyAsync(bb.d_items, bb.h_items, sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(bb.d_count, 0, sizeof(int) * np, c->stream));
+    // Three streams so that consecutive batches' search kernels run back to back: the pair / work-item tables of this batch travel on
+    // `tab_stream` (issued while the previous batch is still searching), the packing / finishing kernels and the meta read-back of this
+    // batch run on `pack_stream` beside the next batch's search kernel.  Buffer set (bi & 1) is free: the host has seen ev_meta of batch bi-2.
+    cudaStream_t ts = c->pipe_streams ? c->tab_stream : c->stream, ps = c->pipe_streams ? c->pack_stream : c->stream;
+    CK(cudaMemcpyAsync(bb.d_pairs, bb.h_pairs, sizeof(PairDev) * np, cudaMemcpyHostToDevice, ts));
+    if (n_items) CK(cudaMemcpyAsync(bb.d_items, bb.h_items, sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ts));
+    if (n_items_real) CK(cudaMemcpyAsync(bb.d_items_real, bb.h_items_real, sizeof(WorkItem) * n_items_real, cudaMemcpyHostToDevice, ts));
+    CK(cudaMemsetAsync(bb.d_count, 0, sizeof(int) * np, ts));
+    CK(cudaMemsetAsync(bb.d_fb_count, 0, sizeof(int), ts));
+    if (c->pipe_streams) { CK(cudaEventRecord(bb.ev_tab, ts)); CK(cudaStreamWaitEvent(c->stream, bb.ev_tab, 0)); }
     cudaEvent_t k0 = timing_event(c, tev_used), k1 = timing_event(c, tev_used);
     CK(cudaEventRecord(k0, c->stream));
     if (n_items && c->tc_variant >= 2) {
       const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
       if (c->tc_variant == 3)
-        tc2::l2_top2_tc2_kernel<16, false><<<grid, 128 + 16 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+        tc2::l2_top2_tc2_kernel<16, false><<<grid, 128 + 16 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
       else if (c->tc_variant == 4)
-        tc2::l2_top2_tc2_kernel<8, true><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+        tc2::l2_top2_tc2_kernel<8, true><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
       else
-        tc2::l2_top2_tc2_kernel<8, false><<<grid, 128 + 8 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused);
+        tc2::l2_top2_tc2_kernel<8, false><<<grid, 128 + 8 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
       ++launches;
     } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);
       tc::l2_top2_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace);
+      ++launches;
+    }
+    if (n_items_real) {
+      // real-valued pairs: filter kernel (re-scoring in-kernel when the items are long enough), stand-alone re-scoring otherwise, then the
+      // exact search of the few queries the error bound could not decide; after that their candidates are final like everyone else's
+      const int grid = 2 * std::min(n_items_real, c->num_sms / 2);
+      tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_REAL><<<grid, 128 + 8 * 32, tc2::Lay<true, true>::SMEM_BYTES, c->stream>>>(
+          c->d_views, bb.d_pairs, bb.d_items_real, n_items_real, bb.d_cands, bb.d_count, ratio_sq, nullptr, 0, c->d_err, (int)fused_real, bb.d_candx, bb.d_fb, bb.d_fb_count, (int)CAND_CAP);
+      ++launches;
+      if (!fused_real) {
+        rescore_real_kernel<<<dim3(np, 4), VERIFY_WARPS_REAL * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_candx, bb.d_count, ratio_sq, c->d_err, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, 0);
+        ++launches;
+      }
+      exact_rows_kernel<<<4 * c->num_sms, XR_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, bb.d_cands, bb.d_count, ratio_sq);
       ++launches;
     }
     if (any_f32) {
@@ -1091,19 +1175,21 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       ++launches;
     }
     CK(cudaEventRecord(k1, c->stream));
+    if (c->pipe_streams) CK(cudaStreamWaitEvent(ps, k1, 0));
     kernel_events.push_back({k0, k1});
-    scan_counts_kernel<<<1, 1024, 0, c->stream>>>(bb.d_count, np, bb.d_off);
-    verify_pack_kernel<<<dim3(np, VERIFY_BLOCKS_PER_PAIR), VERIFY_WARPS * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, bb.d_off, bb.d_out, ratio_sq, c->d_err);
+    scan_counts_kernel<<<1, 256, 0, ps>>>(bb.d_count, np, bb.d_off);
+    verify_pack_kernel<<<dim3(np, VERIFY_BLOCKS_PER_PAIR), VERIFY_WARPS * 32, 0, ps>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_count, bb.d_off, bb.d_out, ratio_sq, c->d_err);
     launches += 2;
     if (dev_fin) {
-      finish_pairs_kernel<<<np, FIN_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, c->d_flags, bb.d_out, bb.d_count, bb.d_off, bb.d_scratch, bb.d_fin, bb.d_fin_count);
+      finish_pairs_kernel<<<np, FIN_THREADS, 0, ps>>>(c->d_views, bb.d_pairs, c->d_flags, bb.d_out, bb.d_count, bb.d_off, bb.d_scratch, bb.d_fin, bb.d_fin_count);
       ++launches;
-      CK(cudaMemcpyAsync(bb.h_meta + 2 * PAIR_CAP + 2, bb.d_fin_count, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(bb.h_meta + 2 * PAIR_CAP + 2, bb.d_fin_count, sizeof(int) * np, cudaMemcpyDeviceToHost, ps));
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(bb.h_meta, bb.d_count, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(bb.h_meta + PAIR_CAP, bb.d_off, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(bb.ev_meta, c->stream));
+    CK(cudaMemcpyAsync(bb.h_meta + 3 * PAIR_CAP + 2, bb.d_fb_count, sizeof(int), cudaMemcpyDeviceToHost, ps));
+    CK(cudaMemcpyAsync(bb.h_meta, bb.d_count, sizeof(int) * np, cudaMemcpyDeviceToHost, ps));
+    CK(cudaMemcpyAsync(bb.h_meta + PAIR_CAP, bb.d_off, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, ps));
+    CK(cudaEventRecord(bb.ev_meta, ps));
     return B200M_OK;
   };
 
@@ -1114,10 +1200,10 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       if (bi >= 2) CK(cudaEventSynchronize(c->buf[bi & 1].ev_meta));   // pinned staging of batch bi-2 consumed by its H2D copies
       if ((rc = enqueue(bi))) return rc;
       // totals are read from the pinned meta buffer once the batch is done; accumulate lazily below
-      if (bi >= 1) { CK(cudaEventSynchronize(c->buf[(bi - 1) & 1].ev_meta)); const Batch& P = batches[bi - 1]; total_records += c->buf[(bi - 1) & 1].h_meta[PAIR_CAP + (P.end - P.begin)]; }
+      if (bi >= 1) { CK(cudaEventSynchronize(c->buf[(bi - 1) & 1].ev_meta)); const Batch& P = batches[bi - 1]; total_records += c->buf[(bi - 1) & 1].h_meta[PAIR_CAP + (P.end - P.begin)]; fallback_rows += c->buf[(bi - 1) & 1].h_meta[3 * PAIR_CAP + 2]; }
     }
     CK(cudaEventRecord(c->ev_end, c->stream));
-    if (!batches.empty()) { const size_t l = batches.size() - 1; CK(cudaEventSynchronize(c->buf[l & 1].ev_meta)); total_records += c->buf[l & 1].h_meta[PAIR_CAP + (batches[l].end - batches[l].begin)]; }
+    if (!batches.empty()) { const size_t l = batches.size() - 1; CK(cudaEventSynchronize(c->buf[l & 1].ev_meta)); total_records += c->buf[l & 1].h_meta[PAIR_CAP + (batches[l].end - batches[l].begin)]; fallback_rows += c->buf[l & 1].h_meta[3 * PAIR_CAP + 2]; }
   } else {
     if (!batches.empty() && (rc = enqueue(0))) return rc;
     for (size_t bi = 0; bi < batches.size(); ++bi) {
@@ -1130,6 +1216,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       }
       CK(cudaEventSynchronize(bb.ev_meta));
       const int total = bb.h_meta[PAIR_CAP + np];
+      fallback_rows += bb.h_meta[3 * PAIR_CAP + 2];
       if (bi >= 2) groups[bi - 2]->wait();       // the tasks of batch bi-2 read this pinned record buffer
       if (total > 0) {
         CK(cudaStreamWaitEvent(c->copy_stream, bb.ev_meta, 0));
@@ -1192,13 +1279,25 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   }
   const double t_gpu_done = now();
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->pack_stream));
   float ms = 0.f;
   CK(cudaEventSynchronize(c->ev_end));
   CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_end));
   c->last_gpu_ms = ms;
   double sk = 0;
   for (auto& e : kernel_events) { float t = 0.f; CK(cudaEventElapsedTime(&t, e.first, e.second)); sk += t; }
+  if (timing && !kernel_events.empty()) {
+    // device timeline of the call: search kernels back to back?  gap = end of one batch's search kernels -> start of the next one's
+    // (packing / finishing kernels, meta copies, the next batch's pair-table copies, and any wait for the host)
+    float lead = 0.f, gaps = 0.f, gmax = 0.f, tail = 0.f;
+    CK(cudaEventElapsedTime(&lead, c->ev_start, kernel_events.front().first));
+    for (size_t k = 0; k + 1 < kernel_events.size(); ++k) { float t = 0.f; CK(cudaEventElapsedTime(&t, kernel_events[k].second, kernel_events[k + 1].first)); gaps += t; gmax = std::max(gmax, t); }
+    CK(cudaEventElapsedTime(&tail, kernel_events.back().second, c->ev_end));
+    fprintf(stderr, "[b200m] device timeline: %zu batches, search kernels %.2f ms, lead-in %.2f, gaps between batches %.2f (max %.2f), tail after the last search kernel %.2f ms\n",
+            kernel_events.size(), sk, lead, gaps, gmax, tail);
+  }
   c->last_search_ms = sk; c->last_launches = launches; c->last_tc_pairs = tc_pairs; c->last_records = total_records;
+  c->last_real_pairs = real_pairs; c->last_fallback_rows = fallback_rows;
   unsigned errs = 0;
   CK(cudaMemcpy(&errs, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost));
   c->err_total = errs;
@@ -1270,6 +1369,8 @@ int b200m_last_launches(const b200m_ctx* c) { return c ? c->last_launches : 0; }
 int b200m_last_tc_pairs(const b200m_ctx* c) { return c ? c->last_tc_pairs : 0; }
 unsigned b200m_exactness_errors(const b200m_ctx* c) { return c ? c->err_total : 0; }
 int64_t b200m_last_records(const b200m_ctx* c) { return c ? c->last_records : 0; }
+int b200m_last_real_tc_pairs(const b200m_ctx* c) { return c ? c->last_real_pairs : 0; }
+int64_t b200m_last_fallback_rows(const b200m_ctx* c) { return c ? c->last_fallback_rows : 0; }
 
 // ---- guided matching (after the path: GeometricFilterMatrix_F_AC.hpp:363-390 -> matching/guidedMatching.hpp:206-268) ----------------
 int b200m_guided_match(b200m_ctx* c, uint32_t view_left, uint32_t view_right, const double* F, double errorTh, double distRatio, b200m_result** out) {
@@ -1554,6 +1655,10 @@ int b200m_multi_match(b200m_multi* m, int n_views, const uint32_t* view_ids, con
 }
 
 // ---- Surface 1: ArrayMatcher ------------------------------------------------------------------------------------
+// Build keeps the dataset RESIDENT in the form the tensor-core kernel reads (fp16 copy, half-norm limbs, tensor maps: the same
+// preparation as an uploaded view), so SearchNeighbours with NN = 2 on 128-D integer-valued descriptors - what RegionsMatcher<ArrayMatcherT>
+// ::Match calls, matching/RegionsMatcher.hpp:140-146 - is one query copy, the preparation kernel, the tcgen05 kernel in its MODE_KNN
+// (both neighbours' chunks kept, every query emitted) and knn_finalize_kernel, out of grow-only scratch: no allocation, one synchronisation.
 int b200m_db_create(b200m_ctx* c, const void* data, int rows, int dim, int dtype, int metric, b200m_db** out) {
   if (!c || !out) return fail(B200M_ERR_ARG, "bad arguments");
   std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
@@ -1562,20 +1667,66 @@ int b200m_db_create(b200m_ctx* c, const void* data, int rows, int dim, int dtype
   if (!data || dim < 1 || dtype < 0 || dtype > 2 || metric < 0 || metric > 2) return fail(B200M_ERR_ARG, "bad database arguments");
   if ((metric == B200M_HAMMING) != (dtype == B200M_BIN)) return fail(B200M_ERR_ARG, "Hamming metric needs binary descriptors and vice versa");
   CK(cudaSetDevice(c->device));
+  int rc = ensure_batch_buffers(c);
+  if (rc) return rc;
   std::unique_ptr<b200m_db> db(new b200m_db());
   db->ctx = c; db->metric = metric;
-  db->v.m = rows; db->v.dim = dim; db->v.dtype = dtype;
+  ViewHost& v = db->v;
+  v.m = rows; v.dim = dim; v.dtype = dtype;
   const size_t esz = dtype == DT_F32 ? 4 : 1;
-  CK(cudaMalloc(&db->v.raw, std::max<size_t>((size_t)rows * dim * esz, 256)));
-  CK(cudaMemcpy(db->v.raw, data, (size_t)rows * dim * esz, cudaMemcpyHostToDevice));
+  if ((rc = alloc_view_buffers(c, v))) return rc;
+  CK(cudaMemcpyAsync(v.raw, data, (size_t)rows * dim * esz, cudaMemcpyHostToDevice, c->stream));
+  if (v.tc_capable()) {
+    uint32_t* d_flag = nullptr;
+    CK(cudaMallocAsync((void**)&d_flag, 4, c->stream));
+    CK(cudaMemsetAsync(d_flag, 0, 4, c->stream));
+    if ((rc = run_prep(c, v, d_flag, c->stream))) return rc;
+    CK(cudaMemcpyAsync(&v.flags, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(d_flag, c->stream);
+    if ((rc = make_view_dev(c, v, db->dev))) return rc;
+  } else {
+    CK(cudaStreamSynchronize(c->stream));         // `data` is the caller's (pageable) memory
+    std::memset(&db->dev, 0, sizeof(db->dev));
+    db->dev.raw = v.raw; db->dev.m = v.m; db->dev.dim = v.dim; db->dev.dtype = v.dtype;
+  }
   *out = db.release();
   return B200M_OK;
 }
 void b200m_db_destroy(b200m_db* db) {
   if (!db) return;
-  cudaSetDevice(db->ctx->device);
-  cudaFree(db->v.raw);
+  b200m_ctx* c = db->ctx;
+  std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
+  cudaSetDevice(c->device);
+  free_view_buffers(c, db->v);
+  cudaStreamSynchronize(c->stream);
   delete db;
+}
+
+// grow-only scratch of b200m_knn: the query batch as a prepared view + the small tables and outputs of one call
+static int ensure_knn_scratch(b200m_ctx* c, int nq, int dim, size_t esz) {
+  KnnScratch& k = c->knn;
+  const size_t raw_bytes = std::max<size_t>((size_t)nq * dim * esz, 256);
+  if (nq <= k.cap && raw_bytes <= k.raw_bytes) return B200M_OK;
+  CK(cudaStreamSynchronize(c->stream));
+  const int cap = std::max(nq, k.cap * 2);
+  const int cap_pad = (cap + tc::BN - 1) / tc::BN * tc::BN;
+  const size_t rb = std::max(raw_bytes, (size_t)cap * dim * esz);
+  for (void* q : {(void*)k.raw, (void*)k.h16, (void*)k.nbh, (void*)k.nrm, (void*)k.aug16, (void*)k.augq16, (void*)k.err, (void*)k.cands, (void*)k.idx, (void*)k.dist, (void*)k.items}) if (q) cudaFree(q);
+  CK(cudaMalloc(&k.raw, rb));
+  CK(cudaMalloc((void**)&k.h16, (size_t)cap_pad * 256));
+  CK(cudaMalloc((void**)&k.nbh, (size_t)cap_pad * 4));
+  CK(cudaMalloc((void**)&k.nrm, (size_t)cap_pad * 4));
+  CK(cudaMalloc((void**)&k.aug16, (size_t)cap_pad * 32));
+  CK(cudaMalloc((void**)&k.augq16, (size_t)cap_pad * 32));
+  CK(cudaMalloc((void**)&k.err, (size_t)cap_pad * 4));
+  CK(cudaMalloc((void**)&k.cands, sizeof(Cand) * (size_t)cap_pad));
+  CK(cudaMalloc((void**)&k.idx, sizeof(int32_t) * 16 * (size_t)cap));       // NN <= 16 on the generic path
+  CK(cudaMalloc((void**)&k.dist, sizeof(uint32_t) * 16 * (size_t)cap));
+  CK(cudaMalloc((void**)&k.items, sizeof(WorkItem) * (size_t)(cap_pad / 256 + 1)));
+  if (!k.small) CK(cudaMalloc((void**)&k.small, 4096));                        // stats (16 B) | flag (4 B) | PairDev | 2 x ViewDev (aligned 128)
+  k.cap = cap; k.raw_bytes = rb;
+  return B200M_OK;
 }
 
 int b200m_knn(b200m_ctx* c, const b200m_db* db, const void* query, int nq, int nn, int32_t* idx, void* dist) {
@@ -1589,40 +1740,73 @@ int b200m_knn(b200m_ctx* c, const b200m_db* db, const void* query, int nq, int n
   if (rc) return rc;
   const ViewHost& v = db->v;
   const size_t esz = v.dtype == DT_F32 ? 4 : 1;
-  void* d_q = nullptr; int32_t* d_idx = nullptr; uint32_t* d_dist = nullptr;
-  CK(cudaMallocAsync(&d_q, std::max<size_t>((size_t)nq * v.dim * esz, 256), c->stream));
-  CK(cudaMallocAsync((void**)&d_idx, sizeof(int32_t) * (size_t)nq * nn, c->stream));
-  CK(cudaMallocAsync((void**)&d_dist, sizeof(uint32_t) * (size_t)nq * nn, c->stream));
-  CK(cudaMemcpyAsync(d_q, query, (size_t)nq * v.dim * esz, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ensure_knn_scratch(c, nq, v.dim, esz))) return rc;
+  KnnScratch& k = c->knn;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(k.raw, query, (size_t)nq * v.dim * esz, cudaMemcpyHostToDevice, st));
+  uint32_t* d_stats = reinterpret_cast<uint32_t*>(k.small);
+  uint32_t* d_flag = d_stats + 4;
+  PairDev* d_pair = reinterpret_cast<PairDev*>(k.small + 64);
+  ViewDev* d_views = reinterpret_cast<ViewDev*>(k.small + 128);
+
+  // ---- tensor-core path: the two nearest neighbours of 128-D integer-valued descriptors (any L2 metric: every sum is exact)
+  bool done = false;
+  if (nn == 2 && v.tc_ok() && !c->force_exact && c->tc_variant == 4 && v.m <= 16 * 0xFFFF) {
+    ViewHost qv;
+    qv.m = nq; qv.dim = v.dim; qv.dtype = v.dtype; qv.m_pad = (nq + tc::BN - 1) / tc::BN * tc::BN;
+    qv.raw = k.raw; qv.h16 = k.h16; qv.nbh = k.nbh; qv.nrm = k.nrm; qv.aug16 = k.aug16; qv.augq16 = k.augq16; qv.err = k.err; qv.stats = d_stats;
+    ViewDev hv[2];
+    hv[0] = db->dev;
+    if ((rc = make_view_dev(c, qv, hv[1]))) return rc;
+    CK(cudaMemsetAsync(d_flag, 0, 4, st));
+    if ((rc = run_prep(c, qv, d_flag, st))) return rc;
+    const int n_items = (nq + 2 * tc2::BM - 1) / (2 * tc2::BM);
+    std::vector<WorkItem> items(n_items);
+    for (int t = 0; t < n_items; ++t) items[t] = WorkItem{0u, (uint32_t)t};
+    const PairDev hp{0u, 1u, (uint32_t)v.m, (uint32_t)nq, 0u, (uint32_t)PM_TC, 0u};
+    CK(cudaMemcpyAsync(d_views, hv, sizeof(hv), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pair, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k.items, items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, st));
+    const int grid = 2 * std::min(n_items, c->num_sms / 2);
+    tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_KNN><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, st>>>(
+        d_views, d_pair, k.items, n_items, k.cands, nullptr, 0.f, nullptr, 0, c->d_err, 0, nullptr, nullptr, nullptr, 0);
+    knn_finalize_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_views, d_pair, k.cands, k.idx, (float*)k.dist, c->d_err);
+    CK(cudaGetLastError());
+    uint32_t qflags = 0;
+    CK(cudaMemcpyAsync(idx, k.idx, sizeof(int32_t) * (size_t)nq * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dist, k.dist, sizeof(float) * (size_t)nq * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&qflags, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&c->err_total, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));               // items / hv / hp are stack objects; results are in the caller's buffers
+    done = (qflags & VF_EXACT_MASK) == 0;        // a query batch outside the exact domain (non-integer, huge values): redo on the exact kernels
+    c->last_tc_pairs = done ? 1 : 0;
+  }
+  if (done) return B200M_OK;
+  c->last_tc_pairs = 0;
+
   const bool tiled_l2 = nn == 2 && v.dim == 128 && v.dtype != DT_BIN && (v.dtype == DT_U8 || db->metric == B200M_L2_VECTORIZED);
   const bool tiled_ham = nn == 2 && v.dim == 64 && v.dtype == DT_BIN;
   if (tiled_l2 || tiled_ham) {
     ViewDev hv[2]; std::memset(hv, 0, sizeof(hv));
     hv[0].raw = v.raw; hv[0].m = v.m; hv[0].dim = v.dim; hv[0].dtype = v.dtype;
-    hv[1].raw = d_q; hv[1].m = nq; hv[1].dim = v.dim; hv[1].dtype = v.dtype;
+    hv[1].raw = k.raw; hv[1].m = nq; hv[1].dim = v.dim; hv[1].dtype = v.dtype;
     const uint32_t mode = tiled_ham ? PM_HAMMING : (v.dtype == DT_F32 ? PM_EXACT_F32 : PM_EXACT_U8);
-    PairDev hp{0u, 1u, (uint32_t)v.m, (uint32_t)nq, 0u, mode};
-    ViewDev* d_v = nullptr; PairDev* d_p = nullptr;
-    CK(cudaMallocAsync((void**)&d_v, sizeof(hv), c->stream));
-    CK(cudaMallocAsync((void**)&d_p, sizeof(hp), c->stream));
-    CK(cudaMemcpyAsync(d_v, hv, sizeof(hv), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_p, &hp, sizeof(hp), cudaMemcpyHostToDevice, c->stream));
-    if (tiled_ham) hamming_top2_kernel<true><<<dim3((nq + HM_TQ - 1) / HM_TQ, 1), HM_TQ, 0, c->stream>>>(d_v, d_p, nullptr, nullptr, 0.f, d_idx, d_dist);
-    else if (v.dtype == DT_F32) exact_top2_kernel<float, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, c->stream>>>(d_v, d_p, mode, nullptr, nullptr, 0.f, d_idx, (float*)d_dist);
-    else exact_top2_kernel<uint8_t, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, c->stream>>>(d_v, d_p, mode, nullptr, nullptr, 0.f, d_idx, (float*)d_dist);
+    const PairDev hp{0u, 1u, (uint32_t)v.m, (uint32_t)nq, 0u, mode, 0u};
+    CK(cudaMemcpyAsync(d_views, hv, sizeof(hv), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pair, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+    if (tiled_ham) hamming_top2_kernel<true><<<dim3((nq + HM_TQ - 1) / HM_TQ, 1), HM_TQ, 0, st>>>(d_views, d_pair, nullptr, nullptr, 0.f, k.idx, k.dist);
+    else if (v.dtype == DT_F32) exact_top2_kernel<float, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, st>>>(d_views, d_pair, mode, nullptr, nullptr, 0.f, k.idx, (float*)k.dist);
+    else exact_top2_kernel<uint8_t, true><<<dim3((nq + EX_TQ - 1) / EX_TQ, 1), 256, EX_SMEM, st>>>(d_views, d_pair, mode, nullptr, nullptr, 0.f, k.idx, (float*)k.dist);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));   // hv/hp are stack objects
-    cudaFreeAsync(d_v, c->stream); cudaFreeAsync(d_p, c->stream);
   } else {
     const int grid = (nq + 3) / 4;
-    if (v.dtype == DT_F32) generic_knn_kernel<float><<<grid, 128, 0, c->stream>>>((const float*)v.raw, v.m, (const float*)d_q, nq, v.dim, nn, db->metric, d_idx, d_dist);
-    else generic_knn_kernel<uint8_t><<<grid, 128, 0, c->stream>>>((const uint8_t*)v.raw, v.m, (const uint8_t*)d_q, nq, v.dim, nn, db->metric, d_idx, d_dist);
+    if (v.dtype == DT_F32) generic_knn_kernel<float><<<grid, 128, 0, st>>>((const float*)v.raw, v.m, (const float*)k.raw, nq, v.dim, nn, db->metric, k.idx, k.dist);
+    else generic_knn_kernel<uint8_t><<<grid, 128, 0, st>>>((const uint8_t*)v.raw, v.m, (const uint8_t*)k.raw, nq, v.dim, nn, db->metric, k.idx, k.dist);
     CK(cudaGetLastError());
   }
-  CK(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(dist, d_dist, sizeof(uint32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFreeAsync(d_q, c->stream); cudaFreeAsync(d_idx, c->stream); cudaFreeAsync(d_dist, c->stream);
+  CK(cudaMemcpyAsync(idx, k.idx, sizeof(int32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(dist, k.dist, sizeof(uint32_t) * (size_t)nq * nn, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return B200M_OK;
 }
 

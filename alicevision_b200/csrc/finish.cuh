@@ -17,28 +17,26 @@ namespace b200m {
 
 // yrank[i] = number of features of the view whose y is smaller than y_i (the position of feature i in the ascending-y order when all
 // y are distinct); sets VF_POS_NONGENERIC in *flags when two features share an x or a y, or a coordinate is NaN.
-constexpr int PR_THREADS = 128, PR_TILE = 1024;
+// O(m^2) comparisons spread over grid (i blocks) x (k ranges): partial counts are added atomically into yrank (zeroed by the
+// caller).  No shared memory on purpose: these launches run on the upload stream WHILE the persistent tensor-core kernel owns
+// every SM with ~193 KB of shared memory per CTA - a block that needs its own shared-memory carve-out would have to wait for that
+// kernel to end (measured: 0.65 ms per view of upload stall); the positions are read as warp-uniform (broadcast) loads instead.
+constexpr int PR_THREADS = 128, PR_KRANGE = 1024;
 __global__ void __launch_bounds__(PR_THREADS)
 pos_rank_kernel(const float2* __restrict__ xy, int m, uint32_t* __restrict__ yrank, uint32_t* __restrict__ flags) {
-  __shared__ float2 tile[PR_TILE];
   const int i = blockIdx.x * PR_THREADS + threadIdx.x;
+  const int k0 = blockIdx.y * PR_KRANGE, k1 = min(k0 + PR_KRANGE, m);
   const float2 me = i < m ? xy[i] : make_float2(0.f, 0.f);
   uint32_t less = 0; bool dup = false;
-  for (int t0 = 0; t0 < m; t0 += PR_TILE) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < PR_TILE && t0 + e < m; e += PR_THREADS) tile[e] = xy[t0 + e];
-    __syncthreads();
-    const int n = min(PR_TILE, m - t0);
-#pragma unroll 4
-    for (int e = 0; e < n; ++e) {
-      const float2 o = tile[e];
-      less += (o.y < me.y) ? 1u : 0u;
-      dup |= (t0 + e != i) && (o.x == me.x || o.y == me.y);
-    }
+#pragma unroll 8
+  for (int k = k0; k < k1; ++k) {
+    const float2 o = __ldg(xy + k);                      // same address on every lane: one broadcast transaction, L1-resident
+    less += (o.y < me.y) ? 1u : 0u;
+    dup |= (k != i) && (o.x == me.x || o.y == me.y);
   }
   if (i < m) {
-    yrank[i] = less;
-    if (dup || me.x != me.x || me.y != me.y) atomicOr(flags, VF_POS_NONGENERIC);
+    if (less) atomicAdd(&yrank[i], less);
+    if (dup || (blockIdx.y == 0 && (me.x != me.x || me.y != me.y))) atomicOr(flags, VF_POS_NONGENERIC);
   }
 }
 

@@ -16,6 +16,20 @@
 //   leader CTA: warp 1 issues tcgen05.mma.cta_group::2; completions are multicast to both CTAs' barriers
 // Barrier homes: q_full / db_full / tm_empty live in the LEADER (TMA bytes of both CTAs and the epilogue arrivals of
 // both CTAs are credited there); q_empty / db_empty / tm_full / nb_full / nb_empty are per CTA.
+//
+// MODE (template): what the epilogue keeps per query row and what leaves the kernel
+//   MODE_MATCH  integer-valued descriptors (exact accumulators): two smallest chunk minima + chunk of the best, ratio pre-test,
+//               candidates re-scored exactly (in-kernel when `fused`) -> final match records.                       [the hot path]
+//   MODE_KNN    the same data, ArrayMatcher surface: chunk of the second best is kept too and EVERY query leaves a candidate
+//               (dense, slot = query row) for knn_finalize_kernel, which needs both neighbours' indices.
+//   MODE_REAL   real-valued fp32 descriptors: the GEMM on the fp16-ROUNDED rows is only a FILTER.  The query's half-norm is folded in
+//               as well (A tile = the query's own limbs, loaded per item), so the accumulator is ||a~ - b~||^2 / 2 >= 0 and the chunk id
+//               rides in the low mantissa bits of the chunk minimum: the FOUR smallest packed minima are kept with 7 integer min/max
+//               per chunk.  |sqrt(d~) - sqrt(d)| <= ||a - a~|| + ||b - b~|| bounds what the rounding can do, so the rows outside the
+//               best chunks are provably out of the top-2 whenever the next chunk minimum is far enough; the exact distances (the
+//               reference's fp32 SSE order, from the original fp32 rows) come from re-scoring those chunks (verify.cuh rescore_real),
+//               and the rare query the bound cannot decide goes to the exact_rows fallback.  Results are bit-identical to the
+//               reference whatever the rounding did.
 #pragma once
 #include "l2_tc.cuh"
 #include "verify.cuh"
@@ -30,21 +44,23 @@ constexpr int DBH_BYTES = 128 * 128 * 2;  // 32 KB: this CTA's half of a databas
 constexpr int AUG_BYTES = 128 * 16 * 2;   // 4 KB: 16 augmentation columns of the same 128 rows (AUG only)
 constexpr int NB_BYTES = BN * 4;
 constexpr int MAX_EPI_WARPS = 16;
+enum : int { MODE_MATCH = 0, MODE_KNN = 1, MODE_REAL = 2 };
 
 // Shared-memory layout. AUG = the database half-norm is folded into the GEMM as a 9th K-step: each database row carries
 // 16 extra fp16 columns [b0, l0, l1, 0...] with ||b||^2/2 = 0.5*b0 + l0 + 2048*l1 (all three exact in fp16), every query
 // row the constants [-0.5, -1, -2048, 0...]; with B negated by the instruction descriptor the accumulator becomes
 // h = ||b||^2/2 - a.b directly.  That removes the half-norm ring, 32 LDS.128 and 64 FADD2 per thread and tile from
 // the epilogue for 12.5 % more tensor work.
-template <bool AUG> struct Lay {
+template <bool AUG, bool REAL = false> struct Lay {
   static constexpr int NS = AUG ? 3 : 4;                             // database smem stages per CTA
   static constexpr int STAGE = DBH_BYTES + (AUG ? AUG_BYTES : 0);
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
-  static constexpr int OFF_NB = OFF_DB + NS * STAGE;                 // non-AUG: half-norm ring; AUG: the constant A tile (4 KB)
-  static constexpr int OFF_MRG = OFF_NB + (AUG ? AUG_BYTES : NS * NB_BYTES);
+  static constexpr int OFF_NB = OFF_DB + NS * STAGE;                 // non-AUG: half-norm ring; AUG: the constant A tile (4 KB); REAL: the query's own limb tile, 2 buffers
+  static constexpr int OFF_MRG = OFF_NB + (AUG ? (REAL ? 2 : 1) * AUG_BYTES : NS * NB_BYTES);
   static constexpr int OFF_VQ = OFF_MRG + 2 * 3 * BM * 16;           // candidate queue: 2 buffers x 128 Cand (32 slots per epilogue quadrant)
-  static constexpr int OFF_VQN = OFF_VQ + 2 * BM * 16;               // 2 x (4 per-quadrant counts + pair index), 32 B each
+  static constexpr int OFF_VQX = OFF_VQ + 2 * BM * 16;               // REAL: 5th word of the queued candidates (p4), 2 x 128 x 4 B
+  static constexpr int OFF_VQN = OFF_VQX + (REAL ? 2 * BM * 4 : 0);  // 2 x (4 per-quadrant counts + pair index), 32 B each
   static constexpr int OFF_BAR = OFF_VQN + 2 * 32;
   static constexpr int NUM_BARS = 2 + 2 + NS + NS + 2 + 2 + NS + NS + 2 + 2;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
@@ -52,13 +68,49 @@ template <bool AUG> struct Lay {
 };
 constexpr int SMEM_BYTES = Lay<false>::SMEM_BYTES;
 
-template <int EPI_WARPS, bool AUG>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp); AUG: see Lay
+// Packed four-smallest list of the real-valued filter (non-negative float bit patterns order like unsigned integers).
+struct Top4 { uint32_t p1, p2, p3, p4; };
+__device__ __forceinline__ void top4_insert(Top4& s, uint32_t pk) {
+  s.p4 = min(s.p4, max(s.p3, pk));
+  s.p3 = min(s.p3, max(s.p2, pk));
+  s.p2 = min(s.p2, max(s.p1, pk));
+  s.p1 = min(s.p1, pk);
+}
+__device__ __forceinline__ void fold_chunk_real(const float* h, uint32_t gid, Top4& s) {
+  float a = ptx::fmin3(h[0], h[1], h[2]);
+  float b = ptx::fmin3(h[3], h[4], h[5]);
+  float c = ptx::fmin3(h[6], h[7], h[8]);
+  float d = ptx::fmin3(h[9], h[10], h[11]);
+  float e = ptx::fmin3(h[12], h[13], h[14]);
+  const float cm = fmaxf(fminf(ptx::fmin3(a, b, c), ptx::fmin3(d, e, h[15])), 0.f);   // d~/2 >= 0 up to accumulation rounding
+  top4_insert(s, (__float_as_uint(cm) & ~REAL_IDMASK) | gid);
+}
+// MODE_KNN: like tc::fold_chunk, plus the chunk of the second smallest minimum
+struct Top2g { float m1, m2; uint32_t g1, g2; };
+__device__ __forceinline__ void fold_chunk_knn(const float* h, uint32_t gid, Top2g& s) {
+  float a = ptx::fmin3(h[0], h[1], h[2]);
+  float b = ptx::fmin3(h[3], h[4], h[5]);
+  float c = ptx::fmin3(h[6], h[7], h[8]);
+  float d = ptx::fmin3(h[9], h[10], h[11]);
+  float e = ptx::fmin3(h[12], h[13], h[14]);
+  const float cm = fminf(ptx::fmin3(a, b, c), ptx::fmin3(d, e, h[15]));
+  const bool lt1 = cm < s.m1, lt2 = cm < s.m2;
+  s.g2 = lt1 ? s.g1 : (lt2 ? gid : s.g2);
+  s.m2 = fminf(s.m2, fmaxf(s.m1, cm));
+  s.g1 = lt1 ? gid : s.g1;
+  s.m1 = fminf(s.m1, cm);
+}
+
+template <int EPI_WARPS, bool AUG, int MODE = MODE_MATCH>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp); AUG: see Lay
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
 l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
-                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count, int fused) {
+                   Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count, int fused,
+                   uint32_t* __restrict__ candx, uint2* __restrict__ fb_list, int* __restrict__ fb_count, int fb_cap) {
   long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
-  using L = Lay<AUG>;
-  constexpr int NS = L::NS, OFF_Q = L::OFF_Q, OFF_DB = L::OFF_DB, OFF_NB = L::OFF_NB, OFF_MRG = L::OFF_MRG, OFF_VQ = L::OFF_VQ,
+  constexpr bool REAL = MODE == MODE_REAL, KNN = MODE == MODE_KNN;
+  static_assert(!(REAL || KNN) || (AUG && EPI_WARPS == 8), "MODE_REAL / MODE_KNN exist for the default variant only");
+  using L = Lay<AUG, REAL>;
+  constexpr int NS = L::NS, OFF_Q = L::OFF_Q, OFF_DB = L::OFF_DB, OFF_NB = L::OFF_NB, OFF_MRG = L::OFF_MRG, OFF_VQ = L::OFF_VQ, OFF_VQX = L::OFF_VQX,
                 OFF_VQN = L::OFF_VQN, OFF_BAR = L::OFF_BAR, OFF_TMEM = L::OFF_TMEM, STAGE = L::STAGE;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
@@ -97,7 +149,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
     ptx::tmem_alloc_2sm(tmem_slot, 512);
     ptx::tmem_relinquish_2sm();
   }
-  if (AUG && warp >= 4 && warp < 8) {
+  if (AUG && !REAL && warp >= 4 && warp < 8) {
     // the constant augmentation tile of the A operand: 128 rows x 16 fp16 in the 32-byte-swizzled K-major layout
     // (16-byte chunk index XOR ((row >> 2) & 1)); logical chunk 0 = [-0.5, -1, -2048, 0, 0, 0, 0, 0], chunk 1 = zeros
     const int r = (warp - 4) * 32 + lane;
@@ -126,10 +178,11 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         const ViewDev* vj = views + p.view_j;
         const int qrow = ((int)w.qtile * 2 + (int)rank) * BM;
         ptx::mbar_wait(&q_empty[qb], qph ^ 1);
-        if (rank == 0) ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * Q_BYTES);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * (Q_BYTES + (REAL ? AUG_BYTES : 0)));
         uint8_t* qs = smem + OFF_Q + qb * Q_BYTES;
         ptx::tma_load_2d_2sm(qs, &vj->tmap128, &q_full[qb], 0, qrow);
         ptx::tma_load_2d_2sm(qs + BM * 128, &vj->tmap128, &q_full[qb], 64, qrow);
+        if (REAL) ptx::tma_load_2d_2sm(smem + OFF_NB + qb * AUG_BYTES, &vj->tmap_augq, &q_full[qb], 0, qrow);   // the query rows' own half-norm limbs
         qb ^= 1; if (qb == 0) qph ^= 1;
         const int ntiles = ((int)p.m_i + BN - 1) / BN;
         for (int t = 0; t < ntiles; ++t) {
@@ -188,7 +241,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
             if (k == (AUG ? 6 : 5) && more) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
           }
           if (AUG)   // 9th K-step: constants x half-norm limbs
-            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB)), ptx::umma_desc_k_sw32(b_base + DBH_BYTES), idesc, 1u);
+            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB) + (REAL ? qb * AUG_BYTES : 0)), ptx::umma_desc_k_sw32(b_base + DBH_BYTES), idesc, 1u);
           ptx::umma_commit_2sm_mc(&db_empty[st], 3);
           ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
           ptx::trace_stamp(trace, 1, tt, 2); ++tt;
@@ -210,15 +263,22 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       const __half* db16 = views[p.view_i].h16;
       const __half* q16 = views[p.view_j].h16;
       const Cand* queue = reinterpret_cast<const Cand*>(smem + OFF_VQ) + par * BM;
+      const uint32_t* queuex = reinterpret_cast<const uint32_t*>(smem + OFF_VQX) + par * BM;
       for (int quad = (warp - 2) * 2; quad < (warp - 2) * 2 + 2; ++quad) {
         const int n = (int)hdr[quad];
         for (int e = 0; e < n; ++e) {
           const Cand k = queue[quad * 32 + e];
           Rec rec;
-          const bool keep = rescore_candidate(db16, q16, p.m_i, k, ratio_sq, lane, err_count, rec);
-          if (keep && lane == 0) {
+          int verdict;                                                          // 0 drop, 1 keep, 2 undecided -> exact_rows fallback
+          if (REAL) verdict = rescore_real(views[p.view_i], views[p.view_j], p.m_i, k, queuex[quad * 32 + e], ratio_sq, lane, err_count, rec);
+          else verdict = rescore_candidate(db16, q16, p.m_i, k, ratio_sq, lane, err_count, rec) ? 1 : 0;
+          if (verdict == 1 && lane == 0) {
             const int slot = atomicAdd(&cand_count[hdr[4]], 1);
             cands[p.cand_base + slot] = Cand{rec.j, rec.i, rec.d1, rec.d2};     // final record, (query, database row) order like the exact kernels
+          }
+          if (REAL && verdict == 2 && lane == 0) {
+            const int slot = atomicAdd(fb_count, 1);
+            if (slot < fb_cap) fb_list[slot] = make_uint2(hdr[4], k.q); else atomicAdd(err_count, 1u);
           }
         }
       }
@@ -240,6 +300,8 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       const PairDev p = pairs[w.pair];
       const int ntiles = ((int)p.m_i + BN - 1) / BN;
       tc::Top2 s{INFINITY, INFINITY, 0u};
+      Top2g sk{INFINITY, INFINITY, 0xFFFFu, 0xFFFFu};                          // MODE_KNN
+      Top4 s4{0x7F800000u | REAL_IDMASK, 0x7F800000u | REAL_IDMASK, 0x7F800000u | REAL_IDMASK, 0x7F800000u | REAL_IDMASK};   // MODE_REAL: +inf, id = none
       for (int t = 0; t < ntiles; ++t) {
         if (!AUG && t == 0) ptx::mbar_wait(&nb_full[st], sph);     // later tiles: already observed at the end of the previous tile
         ptx::trace_stamp(etrace, 2 + colq, tt, 0);
@@ -266,8 +328,9 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
             } else {
               tc::add_halfnorms(cur, nb4 + c * 8, h);
             }
-            tc::fold_chunk(h, gbase + c * 2, s);
-            tc::fold_chunk(h + 16, gbase + c * 2 + 1, s);
+            if (REAL) { fold_chunk_real(h, gbase + c * 2, s4); fold_chunk_real(h + 16, gbase + c * 2 + 1, s4); }
+            else if (KNN) { fold_chunk_knn(h, gbase + c * 2, sk); fold_chunk_knn(h + 16, gbase + c * 2 + 1, sk); }
+            else { tc::fold_chunk(h, gbase + c * 2, s); tc::fold_chunk(h + 16, gbase + c * 2 + 1, s); }
           } else {
             float keepalive = __uint_as_float(cur[0]);
 #pragma unroll
@@ -292,9 +355,59 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       }
       // merge the column groups of each query row, pre-test, emit candidates
       float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * 3 * BM;
-      if (colq > 0) mrg[(colq - 1) * BM + row] = make_float4(s.m1, s.m2, __uint_as_float(s.g1), 0.f);
+      if (colq > 0) {
+        if (REAL) mrg[(colq - 1) * BM + row] = make_float4(__uint_as_float(s4.p1), __uint_as_float(s4.p2), __uint_as_float(s4.p3), __uint_as_float(s4.p4));
+        else if (KNN) mrg[(colq - 1) * BM + row] = make_float4(sk.m1, sk.m2, __uint_as_float(sk.g1), __uint_as_float(sk.g2));
+        else mrg[(colq - 1) * BM + row] = make_float4(s.m1, s.m2, __uint_as_float(s.g1), 0.f);
+      }
       ptx::named_bar_sync(1, EPI_WARPS * 32);
       if (colq == 0) {
+        const uint32_t q = (w.qtile * 2 + rank) * BM + row;
+        if (REAL) {
+#pragma unroll
+          for (int o_ = 0; o_ < NQ - 1; ++o_) {
+            const float4 o = mrg[o_ * BM + row];
+            top4_insert(s4, __float_as_uint(o.x)); top4_insert(s4, __float_as_uint(o.y)); top4_insert(s4, __float_as_uint(o.z)); top4_insert(s4, __float_as_uint(o.w));
+          }
+          bool keep = false;
+          if (q < p.m_j) {
+            // superset pre-test on bounds of the TRUE (reference) distances: lower(best) < r^2 * upper(second smallest chunk minimum)
+            const RealBound rb = real_bound(views[p.view_i], views[p.view_j], q);
+            const float d1t = 2.f * __uint_as_float(s4.p1 & ~REAL_IDMASK), d2t = 2.f * __uint_as_float(s4.p2 & ~REAL_IDMASK);
+            keep = rb.lower(d1t) < __fmul_rn(ratio_sq, rb.upper(d2t));
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+          const int pos = __popc(mask & ((1u << lane) - 1));
+          if (fused) {
+            ptx::mbar_wait(&vq_empty[par], vqph ^ 1);
+            Cand* queue = reinterpret_cast<Cand*>(smem + OFF_VQ) + par * BM + quad * 32;
+            uint32_t* queuex = reinterpret_cast<uint32_t*>(smem + OFF_VQX) + par * BM + quad * 32;
+            if (keep) { queue[pos] = Cand{q, s4.p1, __uint_as_float(s4.p2), __uint_as_float(s4.p3)}; queuex[pos] = s4.p4; }
+            uint32_t* hdr = reinterpret_cast<uint32_t*>(smem + OFF_VQN + par * 32);
+            if (lane == 0) { hdr[quad] = (uint32_t)__popc(mask); if (quad == 0) hdr[4] = w.pair; }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&vq_full[par]);
+          } else if (mask) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cand_count[w.pair], __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) { cands[p.cand_base + base + pos] = Cand{q, s4.p1, __uint_as_float(s4.p2), __uint_as_float(s4.p3)}; candx[p.cand_base + base + pos] = s4.p4; }
+          }
+        } else if (KNN) {
+#pragma unroll
+          for (int o_ = 0; o_ < NQ - 1; ++o_) {
+            const float4 o = mrg[o_ * BM + row];
+            const uint32_t og1 = __float_as_uint(o.z), og2 = __float_as_uint(o.w);
+            if (o.x < sk.m1) {
+              if (sk.m1 <= o.y) { sk.m2 = sk.m1; sk.g2 = sk.g1; } else { sk.m2 = o.y; sk.g2 = og2; }
+              sk.m1 = o.x; sk.g1 = og1;
+            } else if (o.x < sk.m2) { sk.m2 = o.x; sk.g2 = og1; }
+          }
+          if (q < p.m_j) {                                   // dense: every query leaves its two chunks for knn_finalize_kernel
+            const float na = views[p.view_j].nrm[q];
+            cands[p.cand_base + q] = Cand{q, (sk.g1 & 0xFFFFu) | (sk.g2 << 16), fmaf(2.f, sk.m1, na), fmaf(2.f, sk.m2, na)};
+          }
+        } else {
         float m1 = s.m1, m2 = s.m2; uint32_t g1 = s.g1;
 #pragma unroll
         for (int o_ = 0; o_ < NQ - 1; ++o_) {
@@ -303,7 +416,6 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           g1 = (o.x < m1) ? __float_as_uint(o.z) : g1;
           m1 = fminf(m1, o.x);
         }
-        const uint32_t q = (w.qtile * 2 + rank) * BM + row;
         bool keep = false;
         float d1 = 0.f, d2 = 0.f;
         if (q < p.m_j) {
@@ -327,6 +439,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           if (lane == 0) base = atomicAdd(&cand_count[w.pair], __popc(mask));
           base = __shfl_sync(0xffffffffu, base, 0);
           if (keep) cands[p.cand_base + base + __popc(mask & ((1u << lane) - 1))] = Cand{q, g1, d1, d2};
+        }
         }
       }
       par ^= 1; if (par == 0) vqph ^= 1;

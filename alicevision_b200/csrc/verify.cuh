@@ -15,6 +15,8 @@
 
 namespace b200m {
 
+constexpr int VERIFY_WARPS_REAL = 8;
+
 // offsets[p] = exclusive prefix sum of cand_count[0..n); offsets[n] = total. Single block.
 __global__ void scan_counts_kernel(const int* __restrict__ cand_count, int n, int* __restrict__ offsets) {
   __shared__ int carry;
@@ -87,6 +89,238 @@ __device__ __forceinline__ bool rescore_candidate(const __half* __restrict__ db1
   const float d2 = fminf(k.d2, second);
   rec = Rec{k.b * 16 + (uint32_t)arg, k.q, best, d2};
   return best < __fmul_rn(ratio_sq, d2);                                // matching/filters.hpp:60
+}
+
+// ------------------------------------------------------------------------------------------------ real-valued fp32 path
+// The reference's L2_Vectorized<float> (feature/metric.hpp:94-123): four SSE lanes, lane l accumulates s_l += (a-b)*(a-b) over
+// components l, l+4, ... with a separate multiply and add, result ((s0+s1)+s2)+s3.  One thread, one (query, database row) pair.
+// Rows are read in their storage type (integer-valued fp32 views are stored as uchar: same values).
+__device__ __forceinline__ float ref_l2_sse(const ViewDev& vq, uint32_t q, const ViewDev& vd, uint32_t row) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (vq.dtype == DT_F32 && vd.dtype == DT_F32) {
+    const float4* a = reinterpret_cast<const float4*>(vq.raw) + (size_t)q * 32;      // same address on every lane of a warp re-scoring one query
+    const float4* b = reinterpret_cast<const float4*>(vd.raw) + (size_t)row * 32;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const float4 x = __ldg(a + t), y = __ldg(b + t);
+      float d;
+      d = __fsub_rn(x.x, y.x); s0 = __fadd_rn(s0, __fmul_rn(d, d));
+      d = __fsub_rn(x.y, y.y); s1 = __fadd_rn(s1, __fmul_rn(d, d));
+      d = __fsub_rn(x.z, y.z); s2 = __fadd_rn(s2, __fmul_rn(d, d));
+      d = __fsub_rn(x.w, y.w); s3 = __fadd_rn(s3, __fmul_rn(d, d));
+    }
+  } else {
+#pragma unroll 4
+    for (int t = 0; t < 32; ++t) {
+      float d;
+      d = __fsub_rn(view_elem(vq, (size_t)q * 128 + 4 * t + 0), view_elem(vd, (size_t)row * 128 + 4 * t + 0)); s0 = __fadd_rn(s0, __fmul_rn(d, d));
+      d = __fsub_rn(view_elem(vq, (size_t)q * 128 + 4 * t + 1), view_elem(vd, (size_t)row * 128 + 4 * t + 1)); s1 = __fadd_rn(s1, __fmul_rn(d, d));
+      d = __fsub_rn(view_elem(vq, (size_t)q * 128 + 4 * t + 2), view_elem(vd, (size_t)row * 128 + 4 * t + 2)); s2 = __fadd_rn(s2, __fmul_rn(d, d));
+      d = __fsub_rn(view_elem(vq, (size_t)q * 128 + 4 * t + 3), view_elem(vd, (size_t)row * 128 + 4 * t + 3)); s3 = __fadd_rn(s3, __fmul_rn(d, d));
+    }
+  }
+  return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+}
+
+// What the fp16 rounding and the fp32 tensor-core accumulation can do to a distance, per (query row, database view):
+//   d~ = ||a~ - b~||^2 as the filter kernel sees it, d = the reference's float distance of the original rows.
+//   * rounding:      | sqrt(d_exact) - ||a~ - b~|| | <= ||a - a~|| + ||b - b~|| <= eta = err[q] + max err of the database view
+//   * accumulation:  | d~ - ||a~ - b~||^2 | <= sigma: 144 products + limb terms summed in fp32 by the tensor core (each partial result within a
+//                    few ulp of the running magnitude <= S = (||a~||^2 + max||b~||^2)/2 + ||a~|| max||b~||) and the limb residuals (<= 2^-22
+//                    relative per half-norm); budgeted generously as 2^-14 * S on d~ - scale-invariant, like everything else here  (checked on
+//                    the device: every re-scored best row must land inside [lower(p1), upper(p1)], `err_count` otherwise)
+//   * the reference's own float summation: relative 2^-17 (33 roundings of 2^-24 on positive terms)
+//   * the chunk id in the low REAL_IDBITS mantissa bits: the packed value is <= the true one and at most 2^-(23-REAL_IDBITS) below it
+struct RealBound {
+  float eta, sigma;
+  __device__ __forceinline__ float lower(float dt) const {          // every reference distance whose filter value is >= dt is >= lower(dt)
+    const float r = fmaxf(sqrtf(fmaxf(dt - sigma, 0.f)) - eta, 0.f);
+    return r * r * (1.f - 1.f / 65536.f);
+  }
+  __device__ __forceinline__ float upper(float dt) const {          // ... whose (packed) filter value is dt is <= upper(dt)
+    const float r = sqrtf(dt * (1.f + 1.f / 512.f) + sigma) + eta;
+    return r * r * (1.f + 1.f / 65536.f);
+  }
+};
+__device__ __forceinline__ RealBound real_bound(const ViewDev& vi, const ViewDev& vj, uint32_t q) {
+  const float emax = __uint_as_float(vi.stats[0]), nmax = __uint_as_float(vi.stats[1]);
+  const float na = vj.nrm[q];
+  RealBound b;
+  b.eta = (vj.err[q] + emax) * (1.f + 1.f / 1024.f);
+  const float S = 0.5f * (na + nmax) + sqrtf(na * nmax);
+  b.sigma = S * (1.f / 16384.f);
+  return b;
+}
+
+// Warp-level exact re-scoring of one real-valued candidate: k.q = query row, k.b / k.d1 / k.d2 / p4 = the four smallest packed chunk minima
+// (ids in the low bits).  Lane l re-scores row 16*id1 + l (l < 16) or 16*id2 + (l - 16) in the reference's arithmetic; if the third
+// chunk minimum cannot be excluded its 16 rows follow; if the fourth cannot either the query is left to the exact_rows fallback.
+// Returns (on every lane) 0 = fails the ratio test, 1 = final match in `rec`, 2 = undecided.
+__device__ __forceinline__ int rescore_real(const ViewDev& vi, const ViewDev& vj, uint32_t m_i, const Cand& k, uint32_t p4, float ratio_sq, int lane,
+                                            unsigned int* __restrict__ err_count, Rec& rec) {
+  const uint32_t p1 = k.b, p2 = __float_as_uint(k.d1), p3 = __float_as_uint(k.d2);
+  const RealBound rb = real_bound(vi, vj, k.q);
+  const int r = lane & 15;
+  uint32_t row = ((lane < 16 ? p1 : p2) & REAL_IDMASK) * 16 + r;
+  float dist = row < m_i ? ref_l2_sse(vj, k.q, vi, row) : INFINITY;
+  // bound self-check: the best row of the best chunk must lie inside the interval its packed minimum promises
+  {
+    float c1 = lane < 16 ? dist : INFINITY;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) c1 = fminf(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+    const float d1t = 2.f * __uint_as_float(p1 & ~REAL_IDMASK);
+    if (lane == 0 && !(rb.lower(d1t) <= c1 && c1 <= rb.upper(d1t))) atomicAdd(err_count, 1u);
+  }
+  float best = dist; uint32_t arg = row;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const uint32_t oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  float second = (row == arg) ? INFINITY : dist;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) second = fminf(second, __shfl_xor_sync(0xffffffffu, second, o));
+  if (!(rb.lower(2.f * __uint_as_float(p3 & ~REAL_IDMASK)) >= second)) {
+    // the third chunk may hold a row closer than the second best so far: re-score it as well
+    row = (p3 & REAL_IDMASK) * 16 + r;
+    dist = (lane < 16 && row < m_i) ? ref_l2_sse(vj, k.q, vi, row) : INFINITY;
+    float b3 = dist; uint32_t a3 = row;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, b3, o);
+      const uint32_t oa = __shfl_xor_sync(0xffffffffu, a3, o);
+      if (ob < b3 || (ob == b3 && oa < a3)) { b3 = ob; a3 = oa; }
+    }
+    float s3 = (row == a3) ? INFINITY : dist;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) s3 = fminf(s3, __shfl_xor_sync(0xffffffffu, s3, o));
+    b3 = __shfl_sync(0xffffffffu, b3, 0); a3 = __shfl_sync(0xffffffffu, a3, 0); s3 = __shfl_sync(0xffffffffu, s3, 0);
+    if (b3 < best || (b3 == best && a3 < arg)) { second = fminf(best, s3); best = b3; arg = a3; }
+    else second = fminf(second, b3);
+    if (!(rb.lower(2.f * __uint_as_float(p4 & ~REAL_IDMASK)) >= second)) return 2;
+  }
+  rec = Rec{arg, k.q, best, second};
+  return best < __fmul_rn(ratio_sq, second) ? 1 : 0;                     // matching/filters.hpp:60
+}
+
+// Un-fused real-valued pairs (short database images): the filter kernel left its candidates in global memory; re-score them IN PLACE
+// (a final candidate {q, row, d1, d2}, or b = 0xFFFFFFFF = dropped, which the packing kernel turns into the dropped-record marker).
+__global__ void __launch_bounds__(VERIFY_WARPS_REAL * 32)
+rescore_real_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, Cand* __restrict__ cands, const uint32_t* __restrict__ candx,
+                    const int* __restrict__ cand_count, float ratio_sq, unsigned int* __restrict__ err_count, uint2* __restrict__ fb_list,
+                    int* __restrict__ fb_count, int fb_cap, int n_at_launch_unused) {
+  const PairDev p = pairs[blockIdx.x];
+  if (p.mode != PM_TC_REAL) return;
+  const int n = cand_count[blockIdx.x];
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.y * VERIFY_WARPS_REAL + (threadIdx.x >> 5);
+  const int nwarps = gridDim.y * VERIFY_WARPS_REAL;
+  Cand* src = cands + p.cand_base;
+  for (int c = wid; c < n; c += nwarps) {
+    const Cand k = src[c];
+    Rec rec;
+    const int verdict = rescore_real(views[p.view_i], views[p.view_j], p.m_i, k, candx[p.cand_base + c], ratio_sq, lane, err_count, rec);
+    if (lane == 0) {
+      src[c] = verdict == 1 ? Cand{rec.j, rec.i, rec.d1, rec.d2} : Cand{k.q, 0xFFFFFFFFu, 0.f, 0.f};
+      if (verdict == 2) {
+        const int slot = atomicAdd(fb_count, 1);
+        if (slot < fb_cap) fb_list[slot] = make_uint2(blockIdx.x, k.q); else atomicAdd(err_count, 1u);
+      }
+    }
+  }
+}
+
+// Fallback of the real-valued path: the queries whose top-2 the bound could not decide (a few per pair) get the exact search over the WHOLE
+// database image in the reference's arithmetic.  One block per list entry (grid-stride), thread t scans rows t, t + 256, ...;
+// the survivor of the ratio test is appended to its pair's final candidates.
+constexpr int XR_THREADS = 256;
+__global__ void __launch_bounds__(XR_THREADS)
+exact_rows_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint2* __restrict__ fb_list, const int* __restrict__ fb_count,
+                  int fb_cap, Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
+  __shared__ float sv[XR_THREADS / 32][2]; __shared__ uint32_t si[XR_THREADS / 32];
+  const int n = min(*fb_count, fb_cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const uint2 ent = fb_list[e];
+    const PairDev p = pairs[ent.x];
+    const ViewDev& vi = views[p.view_i]; const ViewDev& vj = views[p.view_j];
+    float m1 = INFINITY, m2 = INFINITY; uint32_t i1 = 0xFFFFFFFFu;
+    for (uint32_t row = threadIdx.x; row < p.m_i; row += XR_THREADS) {
+      const float d = ref_l2_sse(vj, ent.y, vi, row);
+      if (d < m1 || (d == m1 && row < i1)) { m2 = m1; m1 = d; i1 = row; } else m2 = fminf(m2, d);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, i1, o);
+      if (o1 < m1 || (o1 == m1 && oi < i1)) { m2 = fminf(m1, o2); m1 = o1; i1 = oi; } else m2 = fminf(m2, o1);
+    }
+    __syncthreads();                                   // previous entry's shared values consumed
+    if (lane == 0) { sv[warp][0] = m1; sv[warp][1] = m2; si[warp] = i1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w2 = 1; w2 < XR_THREADS / 32; ++w2) {
+        const float o1 = sv[w2][0], o2 = sv[w2][1]; const uint32_t oi = si[w2];
+        if (o1 < m1 || (o1 == m1 && oi < i1)) { m2 = fminf(m1, o2); m1 = o1; i1 = oi; } else m2 = fminf(m2, o1);
+      }
+      if (m1 < __fmul_rn(ratio_sq, m2)) {                               // matching/filters.hpp:60
+        const int slot = atomicAdd(&cand_count[ent.x], 1);
+        cands[p.cand_base + slot] = Cand{ent.y, i1, m1, m2};
+      }
+    }
+  }
+}
+
+// ArrayMatcher surface (MODE_KNN of the tensor-core kernel): one warp per query turns its two chunks into the two nearest rows.
+// Lanes 0-15 re-score the rows of the best chunk, lanes 16-31 those of the chunk with the second smallest minimum (integer-valued
+// fp16 data, exact fp32 sums); the two smallest (distance, row) of the 32 are the query's neighbours, ascending.
+__global__ void __launch_bounds__(256)
+knn_finalize_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const Cand* __restrict__ cands, int32_t* __restrict__ idx,
+                    float* __restrict__ dist, unsigned int* __restrict__ err_count) {
+  const PairDev p = pairs[0];
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= (int)p.m_j) return;
+  const Cand k = cands[p.cand_base + q];
+  const uint32_t chunk = lane < 16 ? (k.b & 0xFFFFu) : (k.b >> 16);
+  const uint32_t row = chunk * 16 + (lane & 15);
+  float acc = INFINITY;
+  if (chunk != 0xFFFFu && row < p.m_i) {
+    const uint4* a = reinterpret_cast<const uint4*>(views[p.view_j].h16 + (size_t)q * 128);
+    const uint4* b = reinterpret_cast<const uint4*>(views[p.view_i].h16 + (size_t)row * 128);
+    acc = 0.f;
+#pragma unroll 4
+    for (int v = 0; v < 16; ++v) {
+      const uint4 x = a[v], y = b[v];
+      const __half2* xh = reinterpret_cast<const __half2*>(&x);
+      const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fx = __half22float2(xh[e]), fy = __half22float2(yh[e]);
+        const float d0 = fx.x - fy.x, d1 = fx.y - fy.y;
+        acc = fmaf(d0, d0, acc);
+        acc = fmaf(d1, d1, acc);
+      }
+    }
+  }
+  float b1 = acc; uint32_t a1 = row;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, b1, o); const uint32_t oa = __shfl_xor_sync(0xffffffffu, a1, o);
+    if (ob < b1 || (ob == b1 && oa < a1)) { b1 = ob; a1 = oa; }
+  }
+  float b2 = (row == a1) ? INFINITY : acc; uint32_t a2 = row;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, b2, o); const uint32_t oa = __shfl_xor_sync(0xffffffffu, a2, o);
+    if (ob < b2 || (ob == b2 && oa < a2)) { b2 = ob; a2 = oa; }
+  }
+  if (lane == 0) {
+    if (b1 != k.d1 || b2 > k.d2) atomicAdd(err_count, 1u);            // the tensor-core values are exact on this path (k.d2: second smallest CHUNK minimum)
+    idx[2 * q] = (int32_t)a1; idx[2 * q + 1] = (int32_t)a2;
+    dist[2 * q] = b1; dist[2 * q + 1] = b2;
+  }
 }
 
 constexpr int VERIFY_BLOCKS_PER_PAIR = 4;

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
     "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
-    "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records",
+    "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records", "b200m_last_real_tc_pairs", "b200m_last_fallback_rows",
     "b200m_shard_pairs", "b200m_shard_pairs_2d", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",
     "b200m_multi_last_gpu_ms", "b200m_guided_match", "b200m_guided_match_model",
 ]
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     lib.b200m_last_gpu_ms.restype = C.c_double
     lib.b200m_last_search_kernel_ms.restype = C.c_double
     lib.b200m_last_records.restype = C.c_int64
+    lib.b200m_last_fallback_rows.restype = C.c_int64
     lib.b200m_exactness_errors.restype = C.c_uint
     lib.b200m_multi_last_gpu_ms.restype = C.c_double
     lib.b200m_multi_ctx.restype = C.c_void_p
@@ -148,6 +149,8 @@ class Context:
     def last_tc_pairs(self) -> int: return self.lib.b200m_last_tc_pairs(self._h)
     def exactness_errors(self) -> int: return self.lib.b200m_exactness_errors(self._h)
     def last_records(self) -> int: return self.lib.b200m_last_records(self._h)
+    def last_real_tc_pairs(self) -> int: return self.lib.b200m_last_real_tc_pairs(self._h)
+    def last_fallback_rows(self) -> int: return self.lib.b200m_last_fallback_rows(self._h)
 
 
 _default_ctx: dict[int, Context] = {}
@@ -365,6 +368,8 @@ class ImageCollectionMatcherB200:
             d = np.ascontiguousarray(desc)
             items.append((vid, d, None if xy is None else np.ascontiguousarray(xy, np.float32)))
         codes = {(_dtype_code(d, d.dtype == np.uint8 and self.hamming), d.shape[1] if d.ndim == 2 else 0) for _, d, _ in items}
+        if len(codes) == 0:      # nothing referenced (empty pair list): the empty result
+            return np.zeros((0, 2), np.uint32), np.zeros(1, np.int64), np.zeros(0, MATCH_DTYPE)
         if len(codes) != 1:
             raise B200MatchError("the multi-device path takes views of one descriptor type per call")
         (code, dim), = codes

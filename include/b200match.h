@@ -169,6 +169,11 @@ int b200m_last_tc_pairs(const b200m_ctx* ctx);
 unsigned b200m_exactness_errors(const b200m_ctx* ctx);
 /* total raw records (matches before host finishing) produced by the last call */
 int64_t b200m_last_records(const b200m_ctx* ctx);
+/* pairs of the last call that ran on the tensor-core FILTER kernel for real-valued fp32 descriptors (fp16-rounded GEMM + rigorous error
+ * bound + exact re-scoring in the reference's arithmetic), and the queries among them the bound could not decide, which were searched
+ * exactly over the whole database image (exact_rows fallback) */
+int b200m_last_real_tc_pairs(const b200m_ctx* ctx);
+int64_t b200m_last_fallback_rows(const b200m_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -118,12 +118,17 @@ def test_collection_tensorcore_vs_oracle(ora, dtype, cross, variant):
 
 
 def test_collection_real_valued_exact_path(ora):
+    """Real-valued fp32 on the exact CUDA-core kernel (force_exact), and on the default path (tensor-core filter since round 2)."""
     descs, xys = synth.sift_images(3, 900, np.uint8, seed=41, pool_factor=1.0)
     real = synth.real_valued(descs)
     pairs = synth.exhaustive_pairs(3)
+    want = ora.collection_match(real, xys, pairs, 0.8)
+    got, m = run(real, xys, pairs, force_exact=True)
+    assert m.ctx.last_tc_pairs() == 0 and m.ctx.last_real_tc_pairs() == 0
+    assert_same(got, want)
     got, m = run(real, xys, pairs)
-    assert m.ctx.last_tc_pairs() == 0
-    assert_same(got, ora.collection_match(real, xys, pairs, 0.8))
+    assert m.ctx.last_tc_pairs() == 0 and m.ctx.last_real_tc_pairs() == len(pairs) and m.ctx.exactness_errors() == 0
+    assert_same(got, want)
 
 
 def test_collection_extreme_values_fall_back_to_exact(ora):
@@ -568,3 +573,91 @@ def test_upload_rejects_duplicate_ids_and_survives():
     assert rc == 1 and b"twice" in lib.b200m_last_error()
     m.upload({0: (descs[0], xys[0]), 1: (descs[1], xys[1])})      # the context is still usable
     assert len(m.Match({}, [(0, 1)])) == 1
+
+
+# ---------------------------------------------------------------------------------------------- round 2: real-valued fp32 on the tensor cores
+def _real_images(n, m, seed, scale=1.0, sigma=0.37):
+    descs, xys = synth.sift_images(n, m, np.float32, seed=seed, pool_factor=1.0)
+    real = [np.ascontiguousarray((d * np.float32(scale)).astype(np.float32)) for d in synth.real_valued(descs, sigma=sigma)]
+    return real, xys
+
+
+@pytest.mark.parametrize("case", ["small", "ragged", "unit_norm", "mixed", "duplicates"])
+def test_real_valued_tensorcore_filter_vs_oracle(ora, case):
+    """Real-valued fp32 descriptors on the tensor-core FILTER kernel (MODE_REAL): fp16-rounded GEMM, rigorous error bound, exact
+    re-scoring in the reference's SSE order (feature/metric.hpp:94-123), exact_rows fallback for the undecided queries - bit-identical
+    to the oracle.  small / ragged: stand-alone re-scoring (short images); unit_norm: descriptors scaled by 1/512 (every bound is
+    relative); mixed: integer-valued (stored as uchar) against real-valued views; duplicates: identical rows inside an image."""
+    if case == "unit_norm":
+        descs, xys = _real_images(3, 1500, 301, scale=1.0 / 512.0)
+    else:
+        descs, xys = _real_images(4 if case != "small" else 3, 1500 if case != "small" else 700, 302)
+    if case == "ragged":
+        cut = [1500, 1111, 257, 129]
+        descs = [d[:c] for d, c in zip(descs, cut)]; xys = [x[:c] for x, c in zip(xys, cut)]
+    if case == "mixed":
+        descs[1] = np.ascontiguousarray(np.floor(descs[1]))          # integer-valued fp32 view: staged / stored as uchar
+        descs[3] = np.ascontiguousarray(np.floor(descs[3]))
+    if case == "duplicates":
+        descs[0] = descs[0].copy(); descs[0][100:140] = descs[0][:40]    # d1 == d2 for their matches: never pass the ratio test
+        descs[2] = descs[2].copy(); descs[2][:60] = descs[0][200:260]    # exact copies across images: d1 == 0
+    n = len(descs)
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b] + [(0, 0)]
+    for cross in ((False, True) if case in ("small", "mixed") else (False,)):
+        got, m = run(descs, xys, pairs, cross=cross)
+        want = ora.collection_match(descs, xys, pairs, 0.8, cross)
+        assert_same(got, want)
+        n_int = sum(1 for a, b in pairs if case == "mixed" and a in (1, 3) and b in (1, 3)) * (2 if cross else 1)
+        assert m.ctx.last_real_tc_pairs() == len(pairs) * (2 if cross else 1) - n_int and m.ctx.last_tc_pairs() == n_int
+        assert m.ctx.exactness_errors() == 0                            # incl. the bound self-check of every re-scored candidate
+
+
+def test_real_valued_full_size_fused_vs_oracle(ora):
+    """8192 real-valued features per image: the re-scoring runs INSIDE the filter kernel (fused); every list equals the oracle's and the
+    fallback handles only a small fraction of the queries.  The exact CUDA-core kernel (round-1 path, B200M_REAL_TC=0) agrees."""
+    descs, xys = _real_images(3, 8192, 303)
+    descs[2] = descs[2][:7003]; xys[2] = xys[2][:7003]
+    pairs = [(0, 1), (1, 0), (2, 0), (1, 2), (1, 1)]
+    got, m = run(descs, xys, pairs)
+    want = ora.collection_match(descs, xys, pairs, 0.8)
+    assert_same(got, want)
+    assert m.ctx.last_real_tc_pairs() == len(pairs) and m.ctx.exactness_errors() == 0
+    assert m.ctx.last_fallback_rows() < 0.01 * sum(len(descs[j]) for _, j in pairs), m.ctx.last_fallback_rows()
+    mx = _fresh_matcher({"B200M_REAL_TC": "0"})
+    got2 = dict(mx.Match({i: (descs[i], xys[i]) for i in range(3)}, pairs))
+    assert mx.ctx.last_real_tc_pairs() == 0
+    assert_same(got2, want)
+    mx.ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- round 2: Surface 1 on the tensor cores
+@pytest.mark.parametrize("kind", ["u8", "f32"])
+def test_arraymatcher_tensorcore_knn_8192(ora, kind):
+    """ArrayMatcherB200.SearchNeighbours(NN = 2) on 128-D integer-valued descriptors runs the tcgen05 kernel (MODE_KNN) on the resident,
+    prepared database: distances and both neighbours' indices against ArrayMatcher_bruteForce of the oracle, at 8192 x 8192 and ragged."""
+    ds, _ = synth.sift_images(2, 8192, np.uint8, seed=311, pool_factor=1.0)
+    if kind == "f32":
+        ds = [d.astype(np.float32) for d in ds]
+    for db, q in ((ds[0], ds[1]), (ds[0][:7001], ds[1][:333]), (ds[1][:17], ds[0][:4000])):
+        m = ArrayMatcherB200(matching.L2_VECTORIZED)
+        assert m.Build(db)
+        for rep in range(2):                     # the second call reuses the scratch
+            ok, idx, dist = m.SearchNeighbours(q, NN=2)
+            assert ok and m.ctx.last_tc_pairs() == 1 and m.ctx.exactness_errors() == 0
+        okr, ridx, rdist = ora.knn(db, q, 2, metric="l2_vectorized")
+        assert okr and np.array_equal(dist, rdist)
+        strict1 = rdist[:, 0] < rdist[:, 1]
+        assert np.array_equal(idx[strict1, 0], ridx[strict1, 0])
+        # second neighbour: unique whenever the third distance is larger; compare where the oracle's own second is unambiguous
+        ok3, ridx3, rdist3 = ora.knn(db, q, 3, metric="l2_vectorized") if len(db) >= 3 else (False, None, None)
+        if ok3:
+            strict2 = strict1 & (rdist3[:, 1] < rdist3[:, 2])
+            assert np.array_equal(idx[strict2, 1], ridx3[strict2, 1])
+    # a real-valued query batch against an integer database falls back to the exact kernel, same answers as the oracle
+    m = ArrayMatcherB200(matching.L2_VECTORIZED)
+    if kind == "f32":
+        assert m.Build(ds[0][:3000])
+        qr = synth.real_valued([ds[1][:500]])[0]
+        ok, idx, dist = m.SearchNeighbours(qr, NN=2)
+        okr, ridx, rdist = ora.knn(ds[0][:3000], qr, 2, metric="l2_vectorized")
+        assert ok and m.ctx.last_tc_pairs() == 0 and np.array_equal(dist, rdist)
