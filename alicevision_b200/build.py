@@ -34,6 +34,8 @@ def _nvcc() -> str:
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True
+    if os.environ.get("B200M_NO_BUILD"):       # GPU box: use the library that travelled with the snapshot, whatever the source timestamps say
+        return False
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(f) > t for f in _deps())
 

@@ -204,7 +204,8 @@ struct BatchBuf {
   Rec* d_out = nullptr;
   FinMatch* d_fin = nullptr; int* d_fin_count = nullptr; uint32_t* d_scratch = nullptr;   // device finishing stage (finish.cuh)
   WorkItem* d_items_real = nullptr; WorkItem* h_items_real = nullptr;                     // work items of the real-valued pairs (own launch)
-  uint32_t* d_candx = nullptr; uint2* d_fb = nullptr; int* d_fb_count = nullptr;          // real-valued path: 5th candidate word, fallback list (pair, query)
+  uint32_t* d_candx = nullptr; uint4* d_fb = nullptr; int* d_fb_count = nullptr;          // fallback lists: d_fb_count = [overflow count, total]
+  uint4* d_fb_pair = nullptr; int* d_fb_pair_cnt = nullptr;          // real-valued path: 5th candidate word, fallback list (pair, query)
   PairDev* h_pairs = nullptr; WorkItem* h_items = nullptr; int* h_meta = nullptr; Rec* h_out = nullptr;   // pinned
   cudaEvent_t ev_meta = nullptr, ev_copy = nullptr, ev_tab = nullptr;
 };
@@ -415,8 +416,10 @@ static int ensure_batch_buffers(b200m_ctx* c) {
     CK(cudaMalloc((void**)&b.d_scratch, sizeof(uint32_t) * 2 * SLOT_CAP));
     CK(cudaMalloc((void**)&b.d_items_real, sizeof(WorkItem) * ITEM_CAP));
     CK(cudaMalloc((void**)&b.d_candx, sizeof(uint32_t) * CAND_CAP));
-    CK(cudaMalloc((void**)&b.d_fb, sizeof(uint2) * CAND_CAP));
-    CK(cudaMalloc((void**)&b.d_fb_count, sizeof(int)));
+    CK(cudaMalloc((void**)&b.d_fb, sizeof(uint4) * CAND_CAP));
+    CK(cudaMalloc((void**)&b.d_fb_count, 2 * sizeof(int)));
+    CK(cudaMalloc((void**)&b.d_fb_pair, sizeof(uint4) * (size_t)PAIR_CAP * FB_PER_PAIR));
+    CK(cudaMalloc((void**)&b.d_fb_pair_cnt, sizeof(int) * PAIR_CAP));
     CK(cudaMallocHost((void**)&b.h_items_real, sizeof(WorkItem) * ITEM_CAP));
     CK(cudaMallocHost((void**)&b.h_pairs, sizeof(PairDev) * PAIR_CAP));
     CK(cudaMallocHost((void**)&b.h_items, sizeof(WorkItem) * ITEM_CAP));
@@ -578,6 +581,7 @@ void b200m_ctx_destroy(b200m_ctx* c) {
     cudaFree(b.d_pairs); cudaFree(b.d_items); cudaFree(b.d_cands); cudaFree(b.d_count); cudaFree(b.d_off); cudaFree(b.d_out);
     cudaFree(b.d_fin); cudaFree(b.d_fin_count); cudaFree(b.d_scratch);
     cudaFree(b.d_items_real); cudaFree(b.d_candx); cudaFree(b.d_fb); cudaFree(b.d_fb_count); cudaFreeHost(b.h_items_real);
+    cudaFree(b.d_fb_pair); cudaFree(b.d_fb_pair_cnt);
     cudaFreeHost(b.h_pairs); cudaFreeHost(b.h_items); cudaFreeHost(b.h_meta); cudaFreeHost(b.h_out);
     if (b.ev_meta) cudaEventDestroy(b.ev_meta);
     if (b.ev_copy) cudaEventDestroy(b.ev_copy);
@@ -1122,18 +1126,19 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
     if (n_items) CK(cudaMemcpyAsync(bb.d_items, bb.h_items, sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ts));
     if (n_items_real) CK(cudaMemcpyAsync(bb.d_items_real, bb.h_items_real, sizeof(WorkItem) * n_items_real, cudaMemcpyHostToDevice, ts));
     CK(cudaMemsetAsync(bb.d_count, 0, sizeof(int) * np, ts));
-    CK(cudaMemsetAsync(bb.d_fb_count, 0, sizeof(int), ts));
+    CK(cudaMemsetAsync(bb.d_fb_count, 0, 2 * sizeof(int), ts));
+    if (n_items_real) CK(cudaMemsetAsync(bb.d_fb_pair_cnt, 0, sizeof(int) * np, ts));
     if (c->pipe_streams) { CK(cudaEventRecord(bb.ev_tab, ts)); CK(cudaStreamWaitEvent(c->stream, bb.ev_tab, 0)); }
     cudaEvent_t k0 = timing_event(c, tev_used), k1 = timing_event(c, tev_used);
     CK(cudaEventRecord(k0, c->stream));
     if (n_items && c->tc_variant >= 2) {
       const int grid = 2 * std::min(n_items, c->num_sms / 2);     // CTA pairs (cluster of 2), one pair per work item
       if (c->tc_variant == 3)
-        tc2::l2_top2_tc2_kernel<16, false><<<grid, 128 + 16 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
+        tc2::l2_top2_tc2_kernel<16, false><<<grid, 128 + 16 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, FbSink{});
       else if (c->tc_variant == 4)
-        tc2::l2_top2_tc2_kernel<8, true><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
+        tc2::l2_top2_tc2_kernel<8, true><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, FbSink{});
       else
-        tc2::l2_top2_tc2_kernel<8, false><<<grid, 128 + 8 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, nullptr, nullptr, 0);
+        tc2::l2_top2_tc2_kernel<8, false><<<grid, 128 + 8 * 32, tc2::Lay<false>::SMEM_BYTES, c->stream>>>(c->d_views, bb.d_pairs, bb.d_items, n_items, bb.d_cands, bb.d_count, ratio_sq, c->d_trace, c->dbg_ablate, c->d_err, (int)fused, nullptr, FbSink{});
       ++launches;
     } else if (n_items) {
       const int grid = std::min(n_items, c->num_sms);
@@ -1144,15 +1149,17 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       // real-valued pairs: filter kernel (re-scoring in-kernel when the items are long enough), stand-alone re-scoring otherwise, then the
       // exact search of the few queries the error bound could not decide; after that their candidates are final like everyone else's
       const int grid = 2 * std::min(n_items_real, c->num_sms / 2);
-      tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_REAL><<<grid, 128 + 8 * 32, tc2::Lay<true, true>::SMEM_BYTES, c->stream>>>(
-          c->d_views, bb.d_pairs, bb.d_items_real, n_items_real, bb.d_cands, bb.d_count, ratio_sq, nullptr, 0, c->d_err, (int)fused_real, bb.d_candx, bb.d_fb, bb.d_fb_count, (int)CAND_CAP);
+      const FbSink fbs{bb.d_fb_pair, bb.d_fb_pair_cnt, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, bb.d_fb_count + 1};
+      tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_REAL><<<grid, tc2::block_threads<8, tc2::MODE_REAL>(), tc2::Lay<true, true>::SMEM_BYTES, c->stream>>>(
+          c->d_views, bb.d_pairs, bb.d_items_real, n_items_real, bb.d_cands, bb.d_count, ratio_sq, nullptr, 0, c->d_err, (int)fused_real, bb.d_candx, fbs);
       ++launches;
       if (!fused_real) {
-        rescore_real_kernel<<<dim3(np, 4), VERIFY_WARPS_REAL * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_candx, bb.d_count, ratio_sq, c->d_err, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, 0);
+        rescore_real_kernel<<<dim3(np, 4), VERIFY_WARPS_REAL * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_candx, bb.d_count, ratio_sq, c->d_err, fbs);
         ++launches;
       }
-      exact_rows_kernel<<<4 * c->num_sms, XR_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, bb.d_cands, bb.d_count, ratio_sq);
-      ++launches;
+      exact_rows_pairs_kernel<<<dim3(np, FB_PER_PAIR / XP_MAXQ), XP_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb_pair, bb.d_fb_pair_cnt, bb.d_cands, bb.d_count, ratio_sq);
+      exact_rows_kernel<<<c->num_sms, XR_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, bb.d_cands, bb.d_count, ratio_sq);   // overflow list: normally empty
+      launches += 2;
     }
     if (any_f32) {
       exact_top2_kernel<float, false><<<dim3(max_qblk_exact, np), 256, EX_SMEM, c->stream>>>(c->d_views, bb.d_pairs, PM_EXACT_F32, bb.d_cands, bb.d_count, ratio_sq, nullptr, nullptr);
@@ -1186,7 +1193,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
       CK(cudaMemcpyAsync(bb.h_meta + 2 * PAIR_CAP + 2, bb.d_fin_count, sizeof(int) * np, cudaMemcpyDeviceToHost, ps));
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(bb.h_meta + 3 * PAIR_CAP + 2, bb.d_fb_count, sizeof(int), cudaMemcpyDeviceToHost, ps));
+    CK(cudaMemcpyAsync(bb.h_meta + 3 * PAIR_CAP + 2, bb.d_fb_count + 1, sizeof(int), cudaMemcpyDeviceToHost, ps));
     CK(cudaMemcpyAsync(bb.h_meta, bb.d_count, sizeof(int) * np, cudaMemcpyDeviceToHost, ps));
     CK(cudaMemcpyAsync(bb.h_meta + PAIR_CAP, bb.d_off, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, ps));
     CK(cudaEventRecord(bb.ev_meta, ps));
@@ -1769,7 +1776,7 @@ int b200m_knn(b200m_ctx* c, const b200m_db* db, const void* query, int nq, int n
     CK(cudaMemcpyAsync(k.items, items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, st));
     const int grid = 2 * std::min(n_items, c->num_sms / 2);
     tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_KNN><<<grid, 128 + 8 * 32, tc2::Lay<true>::SMEM_BYTES, st>>>(
-        d_views, d_pair, k.items, n_items, k.cands, nullptr, 0.f, nullptr, 0, c->d_err, 0, nullptr, nullptr, nullptr, 0);
+        d_views, d_pair, k.items, n_items, k.cands, nullptr, 0.f, nullptr, 0, c->d_err, 0, nullptr, FbSink{});
     knn_finalize_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_views, d_pair, k.cands, k.idx, (float*)k.dist, c->d_err);
     CK(cudaGetLastError());
     uint32_t qflags = 0;

@@ -101,13 +101,19 @@ __device__ __forceinline__ void fold_chunk_knn(const float* h, uint32_t gid, Top
   s.m1 = fminf(s.m1, cm);
 }
 
+// The real-valued re-scoring reads 32 fp32 rows per candidate (16 KB, mostly from HBM) and is latency-bound: two warps cannot keep up with
+// the tensor pipe (measured: 135 ms per step instead of 60), so MODE_REAL adds six re-scoring warps behind the epilogue warps.
+constexpr int REAL_EXTRA_VERIFY_WARPS = 6;
+template <int EPI_WARPS, int MODE> constexpr int block_threads() { return 128 + EPI_WARPS * 32 + (MODE == MODE_REAL ? REAL_EXTRA_VERIFY_WARPS * 32 : 0); }
+
 template <int EPI_WARPS, bool AUG, int MODE = MODE_MATCH>   // 8 or 16 epilogue warps per CTA (128 or 64 accumulator columns per warp); AUG: see Lay
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EPI_WARPS * 32, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(block_threads<EPI_WARPS, MODE>(), 1)
 l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const WorkItem* __restrict__ items, int n_items,
                    Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq, long long* __restrict__ trace_buf, int dbg, unsigned int* __restrict__ err_count, int fused,
-                   uint32_t* __restrict__ candx, uint2* __restrict__ fb_list, int* __restrict__ fb_count, int fb_cap) {
+                   uint32_t* __restrict__ candx, FbSink fb) {
   long long* trace = (blockIdx.x == 0) ? trace_buf : nullptr;   // dbg (ablation, debug only): 1 = skip epilogue math, 2 = also skip TMEM loads
   constexpr bool REAL = MODE == MODE_REAL, KNN = MODE == MODE_KNN;
+  constexpr int VERIFY_WARPS_K = REAL ? 2 + REAL_EXTRA_VERIFY_WARPS : 2;   // warps 2, 3 (+ the warps behind the epilogue warps)
   static_assert(!(REAL || KNN) || (AUG && EPI_WARPS == 8), "MODE_REAL / MODE_KNN exist for the default variant only");
   using L = Lay<AUG, REAL>;
   constexpr int NS = L::NS, OFF_Q = L::OFF_Q, OFF_DB = L::OFF_DB, OFF_NB = L::OFF_NB, OFF_MRG = L::OFF_MRG, OFF_VQ = L::OFF_VQ, OFF_VQX = L::OFF_VQX,
@@ -138,7 +144,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
       ptx::mbar_init(&tm_full[i], 1); ptx::mbar_init(&tm_empty[i], 2 * EPI_WARPS);
     }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&vq_full[i], 4); ptx::mbar_init(&vq_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&vq_full[i], 4); ptx::mbar_init(&vq_empty[i], VERIFY_WARPS_K); }
     for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&db_full[i], 1); ptx::mbar_init(&db_empty[i], 1);
       ptx::mbar_init(&nb_full[i], 1); ptx::mbar_init(&nb_empty[i], EPI_WARPS);
@@ -251,7 +257,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         qb ^= 1; if (qb == 0) qph ^= 1;
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 2 || warp == 3 || warp >= 4 + EPI_WARPS) {
     // ------------------------------------------------------------------ exactness pass of the previous item (2 warps)
     // fused == 0 (short database images: an item lasts only a few tiles, two warps cannot hide the re-scoring latency):
     // the epilogue writes its candidates to global memory and the stand-alone exactness kernel handles them.
@@ -264,9 +270,13 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
       const __half* q16 = views[p.view_j].h16;
       const Cand* queue = reinterpret_cast<const Cand*>(smem + OFF_VQ) + par * BM;
       const uint32_t* queuex = reinterpret_cast<const uint32_t*>(smem + OFF_VQX) + par * BM;
-      for (int quad = (warp - 2) * 2; quad < (warp - 2) * 2 + 2; ++quad) {
+      // MATCH: warp 2 serves quadrants 0-1, warp 3 quadrants 2-3.  REAL (8 warps): two warps per quadrant, alternate entries.
+      const int vw = warp < 4 ? warp - 2 : warp - (4 + EPI_WARPS) + 2;
+      const int quad_lo = REAL ? (vw & 3) : vw * 2, quad_hi = REAL ? quad_lo + 1 : quad_lo + 2;
+      const int e_first = REAL ? (vw >> 2) : 0, e_step = REAL ? 2 : 1;
+      for (int quad = quad_lo; quad < quad_hi; ++quad) {
         const int n = (int)hdr[quad];
-        for (int e = 0; e < n; ++e) {
+        for (int e = e_first; e < n; e += e_step) {
           const Cand k = queue[quad * 32 + e];
           Rec rec;
           int verdict;                                                          // 0 drop, 1 keep, 2 undecided -> exact_rows fallback
@@ -276,17 +286,14 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
             const int slot = atomicAdd(&cand_count[hdr[4]], 1);
             cands[p.cand_base + slot] = Cand{rec.j, rec.i, rec.d1, rec.d2};     // final record, (query, database row) order like the exact kernels
           }
-          if (REAL && verdict == 2 && lane == 0) {
-            const int slot = atomicAdd(fb_count, 1);
-            if (slot < fb_cap) fb_list[slot] = make_uint2(hdr[4], k.q); else atomicAdd(err_count, 1u);
-          }
+          if (REAL && verdict == 2 && lane == 0) fb_push(fb, hdr[4], k.q, 0u, 0u, err_count);   // no slot of its own: the fallback appends
         }
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&vq_empty[par]);
       par ^= 1; if (par == 0) vph ^= 1;
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (EPI_WARPS warps per CTA, own 128 rows)
     constexpr int NQ = EPI_WARPS / 4;            // column groups per stage (2 or 4)
     constexpr int COLS = BN / NQ;                // accumulator columns per warp (128 or 64)
@@ -320,6 +327,13 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
           uint32_t (&cur)[32] = (c & 1) ? rb : ra;
           uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
           if (c + 1 < COLS / 32) ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, nxt);
+          else {
+            // every TMEM load of this stage has completed (wait::ld at the end of the previous round): hand the stage back to the MMA
+            // issuer BEFORE folding the last 32 columns - the serial chain MMA(t) -> epilogue(t) -> MMA(t+2) is what bounds the kernel
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(&tm_empty[ac], 0);     // leader: this CTA's rows of TMEM stage ac are drained
+          }
           if (dbg == 0) {
             float h[32];
             if (AUG) {
@@ -341,12 +355,13 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         }
         }
         ptx::trace_stamp(etrace, 2 + colq, tt, 2); ++tt;
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (!AUG) ptx::mbar_arrive(&nb_empty[st]);      // local: the half-norm buffer may be overwritten
-          ptx::mbar_arrive_cluster(&tm_empty[ac], 0);     // leader: this CTA's rows of TMEM stage ac are drained
+        if (dbg >= 2) {                                     // ablation mode without TMEM loads: nothing released the stage above
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(&tm_empty[ac], 0);
         }
+        __syncwarp();
+        if (!AUG && lane == 0) ptx::mbar_arrive(&nb_empty[st]);      // local: the half-norm buffer may be overwritten
         ac ^= 1; if (ac == 0) aph ^= 1;
         if (++st == NS) { st = 0; sph ^= 1; }
         // the next tile's half-norms landed long ago; observing their barrier now (while the tensor pipe is still busy with

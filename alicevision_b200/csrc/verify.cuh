@@ -17,6 +17,19 @@ namespace b200m {
 
 constexpr int VERIFY_WARPS_REAL = 8;
 
+// Where the real-valued path parks the queries its error bound could not decide (x = pair of the batch, y = query row, z = the candidate
+// slot to write the answer to when w != 0): FB_PER_PAIR slots per pair, which the per-pair fallback kernel consumes with the database image
+// read once per group of queries, and a global overflow list for the (pathological) pair that flags more.
+constexpr int FB_PER_PAIR = 64;
+struct FbSink { uint4* pair_list; int* pair_cnt; uint4* list; int* count; int cap; int* total; };
+__device__ __forceinline__ void fb_push(const FbSink& s, uint32_t pair, uint32_t q, uint32_t slot, uint32_t has_slot, unsigned int* err_count) {
+  atomicAdd(s.total, 1);
+  const int k = atomicAdd(&s.pair_cnt[pair], 1);
+  if (k < FB_PER_PAIR) { s.pair_list[(size_t)pair * FB_PER_PAIR + k] = make_uint4(pair, q, slot, has_slot); return; }
+  const int g = atomicAdd(s.count, 1);
+  if (g < s.cap) s.list[g] = make_uint4(pair, q, slot, has_slot); else atomicAdd(err_count, 1u);
+}
+
 // offsets[p] = exclusive prefix sum of cand_count[0..n); offsets[n] = total. Single block.
 __global__ void scan_counts_kernel(const int* __restrict__ cand_count, int n, int* __restrict__ offsets) {
   __shared__ int carry;
@@ -208,8 +221,7 @@ __device__ __forceinline__ int rescore_real(const ViewDev& vi, const ViewDev& vj
 // (a final candidate {q, row, d1, d2}, or b = 0xFFFFFFFF = dropped, which the packing kernel turns into the dropped-record marker).
 __global__ void __launch_bounds__(VERIFY_WARPS_REAL * 32)
 rescore_real_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, Cand* __restrict__ cands, const uint32_t* __restrict__ candx,
-                    const int* __restrict__ cand_count, float ratio_sq, unsigned int* __restrict__ err_count, uint2* __restrict__ fb_list,
-                    int* __restrict__ fb_count, int fb_cap, int n_at_launch_unused) {
+                    const int* __restrict__ cand_count, float ratio_sq, unsigned int* __restrict__ err_count, FbSink fb) {
   const PairDev p = pairs[blockIdx.x];
   if (p.mode != PM_TC_REAL) return;
   const int n = cand_count[blockIdx.x];
@@ -223,26 +235,119 @@ rescore_real_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict
     const int verdict = rescore_real(views[p.view_i], views[p.view_j], p.m_i, k, candx[p.cand_base + c], ratio_sq, lane, err_count, rec);
     if (lane == 0) {
       src[c] = verdict == 1 ? Cand{rec.j, rec.i, rec.d1, rec.d2} : Cand{k.q, 0xFFFFFFFFu, 0.f, 0.f};
-      if (verdict == 2) {
-        const int slot = atomicAdd(fb_count, 1);
-        if (slot < fb_cap) fb_list[slot] = make_uint2(blockIdx.x, k.q); else atomicAdd(err_count, 1u);
+      // the fallback writes its answer into THIS slot (the pair's candidate region has no room to append: a self pair fills every slot)
+      if (verdict == 2) fb_push(fb, blockIdx.x, k.q, (uint32_t)c, 1u, err_count);
+    }
+  }
+}
+
+// Fallback of the real-valued path, per pair: the flagged queries of one pair (a few; FB_PER_PAIR at most here) against the whole database
+// image in the reference's arithmetic.  One block per (pair, group of XP_MAXQ queries); the database rows stream through shared memory in coalesced 64-row tiles
+// (read ONCE per group of XR_MAXQ queries); thread (r, l) owns SSE lane l of tile row r: s_l += (q - row)^2 over components l, l+4, ...
+// in order, the four lanes of a row combined as ((s0+s1)+s2)+s3 (feature/metric.hpp:100-116).
+constexpr int XP_THREADS = 256, XP_ROWS = 64, XP_LD = 132, XP_MAXQ = 8;
+__global__ void __launch_bounds__(XP_THREADS)
+exact_rows_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint4* __restrict__ pair_list, const int* __restrict__ pair_cnt,
+                        Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
+  const PairDev p = pairs[blockIdx.x];
+  if (p.mode != PM_TC_REAL) return;
+  const int n_all = min(pair_cnt[blockIdx.x], FB_PER_PAIR);
+  if (n_all == 0) return;
+  __shared__ float tile[XP_ROWS * XP_LD];
+  __shared__ float qs[XP_MAXQ * 128];
+  __shared__ float rm1[XP_MAXQ][XP_THREADS / 32], rm2[XP_MAXQ][XP_THREADS / 32];
+  __shared__ uint32_t ri1[XP_MAXQ][XP_THREADS / 32];
+  const ViewDev& vi = views[p.view_i]; const ViewDev& vj = views[p.view_j];
+  const int tid = threadIdx.x, r = tid >> 2, l = tid & 3, lane = tid & 31, warp = tid >> 5;
+  const unsigned gmask = 0xFu << (lane & ~3);
+  {                                          // grid.y = FB_PER_PAIR / XP_MAXQ: one block per group of XP_MAXQ flagged queries of the pair
+    const int e0 = blockIdx.y * XP_MAXQ;
+    if (e0 >= n_all) return;
+    const int ne = min(XP_MAXQ, n_all - e0);
+    for (int k = tid; k < ne * 128; k += XP_THREADS) qs[k] = view_elem(vj, (size_t)pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + (k >> 7)].y * 128 + (k & 127));
+    float m1[XP_MAXQ], m2[XP_MAXQ]; uint32_t i1[XP_MAXQ];
+#pragma unroll
+    for (int e = 0; e < XP_MAXQ; ++e) { m1[e] = INFINITY; m2[e] = INFINITY; i1[e] = 0xFFFFFFFFu; }
+    for (uint32_t row0 = 0; row0 < p.m_i; row0 += XP_ROWS) {
+      __syncthreads();
+      for (int k = tid; k < XP_ROWS * 32; k += XP_THREADS) {          // 64 rows x 32 float4, coalesced
+        const int rr = k >> 5, c4 = k & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + rr < p.m_i) {
+          const size_t base = (size_t)(row0 + rr) * 128 + c4 * 4;
+          if (vi.dtype == DT_F32) v = __ldg(reinterpret_cast<const float4*>(vi.raw) + (base >> 2));
+          else v = make_float4(view_elem(vi, base), view_elem(vi, base + 1), view_elem(vi, base + 2), view_elem(vi, base + 3));
+        }
+        *reinterpret_cast<float4*>(&tile[rr * XP_LD + c4 * 4]) = v;
+      }
+      __syncthreads();
+      float s[XP_MAXQ];
+#pragma unroll
+      for (int e = 0; e < XP_MAXQ; ++e) s[e] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < 32; ++t) {
+        const float tv = tile[r * XP_LD + 4 * t + l];
+#pragma unroll
+        for (int e = 0; e < XP_MAXQ; ++e) {
+          if (e < ne) { const float d = __fsub_rn(qs[e * 128 + 4 * t + l], tv); s[e] = __fadd_rn(s[e], __fmul_rn(d, d)); }
+        }
+      }
+      const uint32_t row = row0 + r;
+#pragma unroll
+      for (int e = 0; e < XP_MAXQ; ++e) {
+        if (e < ne) {
+          const float s1 = __shfl_xor_sync(gmask, s[e], 1);
+          const float pr = (l & 1) ? __fadd_rn(s1, s[e]) : __fadd_rn(s[e], s1);          // s0+s1 on lanes 0,1 ; s2+s3 on lanes 2,3
+          const float s01 = __shfl_sync(gmask, pr, 0, 4);
+          const float s2 = __shfl_sync(gmask, s[e], 2, 4), s3 = __shfl_sync(gmask, s[e], 3, 4);
+          const float d = __fadd_rn(__fadd_rn(s01, s2), s3);
+          if (l == 0 && row < p.m_i) {
+            if (d < m1[e] || (d == m1[e] && row < i1[e])) { m2[e] = m1[e]; m1[e] = d; i1[e] = row; } else m2[e] = fminf(m2[e], d);
+          }
+        }
+      }
+    }
+    // reduce the per-thread top-2 (held by the l == 0 threads) over the block
+#pragma unroll
+    for (int e = 0; e < XP_MAXQ; ++e) {
+      float a1 = m1[e], a2 = m2[e]; uint32_t ai = i1[e];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, a1, o), o2 = __shfl_xor_sync(0xffffffffu, a2, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, ai, o);
+        if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
+      }
+      if (lane == 0) { rm1[e][warp] = a1; rm2[e][warp] = a2; ri1[e][warp] = ai; }
+    }
+    __syncthreads();
+    if (tid < ne) {
+      float a1 = rm1[tid][0], a2 = rm2[tid][0]; uint32_t ai = ri1[tid][0];
+      for (int w2 = 1; w2 < XP_THREADS / 32; ++w2) {
+        const float o1 = rm1[tid][w2], o2 = rm2[tid][w2]; const uint32_t oi = ri1[tid][w2];
+        if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
+      }
+      const uint4 ent = pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + tid];
+      if (a1 < __fmul_rn(ratio_sq, a2)) {                                // matching/filters.hpp:60
+        const int slot = ent.w ? (int)ent.z : atomicAdd(&cand_count[blockIdx.x], 1);
+        cands[p.cand_base + slot] = Cand{ent.y, ai, a1, a2};
       }
     }
   }
 }
 
-// Fallback of the real-valued path: the queries whose top-2 the bound could not decide (a few per pair) get the exact search over the WHOLE
+// The same for the overflow list (a pair that flagged more than FB_PER_PAIR queries): the queries whose top-2 the bound could not decide get the exact search over the WHOLE
 // database image in the reference's arithmetic.  One block per list entry (grid-stride), thread t scans rows t, t + 256, ...;
-// the survivor of the ratio test is appended to its pair's final candidates.
+// the survivor of the ratio test goes to the entry's own candidate slot (stand-alone re-scoring: ent.w = 1, slot ent.z holds the
+// "dropped" marker until then) or is appended to the pair's final candidates (in-kernel re-scoring: only final candidates were emitted).
 constexpr int XR_THREADS = 256;
 __global__ void __launch_bounds__(XR_THREADS)
-exact_rows_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint2* __restrict__ fb_list, const int* __restrict__ fb_count,
+exact_rows_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint4* __restrict__ fb_list, const int* __restrict__ fb_count,
                   int fb_cap, Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
   __shared__ float sv[XR_THREADS / 32][2]; __shared__ uint32_t si[XR_THREADS / 32];
   const int n = min(*fb_count, fb_cap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
-    const uint2 ent = fb_list[e];
+    const uint4 ent = fb_list[e];
     const PairDev p = pairs[ent.x];
     const ViewDev& vi = views[p.view_i]; const ViewDev& vj = views[p.view_j];
     float m1 = INFINITY, m2 = INFINITY; uint32_t i1 = 0xFFFFFFFFu;
@@ -265,7 +370,7 @@ exact_rows_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__
         if (o1 < m1 || (o1 == m1 && oi < i1)) { m2 = fminf(m1, o2); m1 = o1; i1 = oi; } else m2 = fminf(m2, o1);
       }
       if (m1 < __fmul_rn(ratio_sq, m2)) {                               // matching/filters.hpp:60
-        const int slot = atomicAdd(&cand_count[ent.x], 1);
+        const int slot = ent.w ? (int)ent.z : atomicAdd(&cand_count[ent.x], 1);
         cands[p.cand_base + slot] = Cand{ent.y, i1, m1, m2};
       }
     }

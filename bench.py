@@ -382,7 +382,7 @@ def main():
     barrier()
     t1w = time.time()
     clocks = sampler.stop(t0w, t1w) if sampler else None
-    tc_pairs = ctx.last_tc_pairs(); errs = ctx.exactness_errors()
+    tc_pairs = ctx.last_tc_pairs(); errs = ctx.exactness_errors(); real_pairs = ctx.last_real_tc_pairs(); fb_rows = ctx.last_fallback_rows()
 
     # ---- e2e: host buffers -> upload -> match -> D2H -> finishing -> result arrays -------------------------------------
     e2e_s = 0.0; h2d = 0; d2h = 0; e2e_steps = 0
@@ -405,15 +405,15 @@ def main():
 
     # ---- reduce over ranks (max time, total pairs) ------------------------------------------------------------------
     stats = torch.tensor([gpu_ms / args.steps, search_ms / args.steps, (t1w - t0w) * 1e3 / args.steps, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(len(mine)), float(launches), float(records), float(errs), float(tc_pairs), float(h2d), float(d2h), float(len(needed))],
-                       dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(len(mine)), float(launches), float(records), float(errs), float(tc_pairs), float(h2d), float(d2h), float(len(needed)),
+                        float(real_pairs), float(fb_rows)], dtype=torch.float64, device="cuda")
     mx = torch.tensor([float(len(mine)), float(len(needed))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     ms_step, ms_search, ms_wall, ms_e2e = stats.tolist()
-    n_pairs, launches, records, errs, tc_pairs, h2d, d2h, views_sum = tot.tolist()
+    n_pairs, launches, records, errs, tc_pairs, h2d, d2h, views_sum, real_pairs, fb_rows = tot.tolist()
 
     if rank == 0:
         M = args.features
@@ -424,14 +424,17 @@ def main():
         out = {
             "metric": metric_name(args), "value": n_pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.config == "1" else "strong", "vs_baseline": None,
-            "dtype": "u32-popcount" if hamming else ("f16 (fp16 operands, fp32 accumulate; exact on integer-valued SIFT)" if args.data == "int" else "f32 (real-valued descriptors)"),
+            "dtype": "u32-popcount" if hamming else ("f16 (fp16 operands, fp32 accumulate; exact on integer-valued SIFT)" if args.data == "int" else
+                                                     "f32 results (fp16-rounded tensor-core filter + exact fp32 re-scoring)" if real_pairs > 0 else "f32 (real-valued descriptors, CUDA cores)"),
             "data": "synthetic",
             "config": {"workload": workload_text(args, n_img, n_pairs),
                        "pairs_per_gpu": n_pairs / world, "max_pairs_on_a_gpu": mx[0].item(), "views_per_gpu": views_sum / world, "max_views_on_a_gpu": mx[1].item(),
                        "sharding": ("2-D blocks of the pair matrix (b200m_shard_pairs_2d)" if args.sharding == "2d" else "pairs dealt round-robin by database image") + ", no collective on the data path",
                        "l2_policy": f"inputs larger than L2 ({mx[1].item() * M * (64 if hamming else 256) / 1e6:.0f} MB of resident descriptors per GPU vs 126 MB L2)",
                        "value_timing": "CUDA events: first enqueue of the step -> last match list landed in pinned host memory (b200m_match_pairs STAGE_FULL on resident views)",
-                       "tensor_core_pairs": tc_pairs, "exactness_errors": errs, "wall_ms_per_step": ms_wall, "records_per_step": records / args.steps,
+                       "tensor_core_pairs": tc_pairs, "real_valued_tensor_core_pairs": real_pairs,
+                       "fallback_rows_per_step": fb_rows, "fallback_rows_fraction_of_queries": (fb_rows / (real_pairs * M)) if real_pairs else 0.0,
+                       "exactness_errors": errs, "wall_ms_per_step": ms_wall, "records_per_step": records / args.steps,
                        "host": cores_info(), "numa": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": (n_pairs / (ms_e2e * 1e-3)) if ms_e2e > 0 else None, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -450,7 +453,9 @@ def main():
         else:
             tr = ncu_traffic("l2_top2_tc2_kernel") if (args.tc_variant == 4 and M == 8192 and tc_pairs > 0) else None
             kern = {1: "tc::l2_top2_tc_kernel", 2: "tc2::l2_top2_tc2_kernel<8,false> (cta_group::2)", 3: "tc2::l2_top2_tc2_kernel<16,false> (cta_group::2)",
-                    4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant] if tc_pairs > 0 else "exact_top2_kernel<float> (CUDA cores, reference summation order)"
+                    4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant] if tc_pairs > 0 else (
+                        "tc2::l2_top2_tc2_kernel<8,true,MODE_REAL> (cta_group::2, fp16-rounded filter GEMM, K=128+16) + exact re-scoring in the reference's fp32 order + exact_rows fallback"
+                        if real_pairs > 0 else "exact_top2_kernel<float> (CUDA cores, reference summation order)")
             out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                                "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_note": tr["note"] if tr else None,
                                "kernel": kern, "peak_source": peak_src, "flop_per_pair": flop_pair, "kernel_ms_per_step": ms_search}
