@@ -175,6 +175,7 @@ struct ViewHost {
   int m = 0, dim = 0, dtype = 0, m_pad = 0;
   void* raw = nullptr; __half* h16 = nullptr; float* nbh = nullptr; float* nrm = nullptr; __half* aug16 = nullptr;
   __half* augq16 = nullptr; float* err = nullptr; uint32_t* stats = nullptr;   // real-valued tensor-core path (prep.cuh): query-side limbs, rounding-error bounds
+  void* arena = nullptr; void* raw_own = nullptr;     // the one allocation all device buffers of the view live in; a separately owned `raw`
   bool stored_u8 = false;     // dtype == DT_F32 whose values are integers in 0..255: staged and kept on the device as uchar (hostconv.hpp)
   float* d_xy = nullptr; uint32_t* d_yrank = nullptr;   // positions + rank of y on the device (device finishing stage, finish.cuh)
   bool failed = false;        // its upload job failed: the device buffers were never filled
@@ -286,37 +287,36 @@ struct b200m_result {
 
 // ------------------------------------------------------------------------------------------------ helpers
 // Device buffers of one view (stream-ordered allocations out of the default pool).
+// ONE stream-ordered allocation per view, carved into its buffers (a view of 1024 features paid more for its ten allocations and ten
+// frees than for its copy): raw | h16 | nbh | nrm | aug16 | augq16 | err | stats | yrank | xy, each 256-byte aligned; stats and yrank are
+// adjacent so that one memset zeroes both.
 static int alloc_view_buffers(b200m_ctx* c, ViewHost& v) {
   const size_t esz = v.store_dtype() == DT_F32 ? 4 : 1;
-  const size_t bytes = (size_t)v.m * v.dim * esz;
-  CK(cudaMallocAsync(&v.raw, std::max<size_t>(bytes, 256), c->stream));
-  if (!v.xy.empty()) {
-    CK(cudaMallocAsync((void**)&v.d_xy, (size_t)v.m * 8, c->stream));
-    CK(cudaMallocAsync((void**)&v.d_yrank, (size_t)v.m * 4, c->stream));
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const bool tcv = v.tc_capable(), pos = !v.xy.empty();
+  if (tcv) v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += al(std::max<size_t>(bytes, 1)); return o; };
+  const size_t o_raw = take(std::max<size_t>((size_t)v.m * v.dim * esz, 256));
+  const size_t o_h16 = tcv ? take((size_t)v.m * 128 * 2) : 0, o_nbh = tcv ? take((size_t)v.m_pad * 4) : 0, o_nrm = tcv ? take((size_t)v.m_pad * 4) : 0;
+  const size_t o_aug = tcv ? take((size_t)v.m_pad * 32) : 0, o_augq = tcv ? take((size_t)v.m_pad * 32) : 0, o_err = tcv ? take((size_t)v.m_pad * 4) : 0;
+  const size_t o_stats = tcv ? take(16) : 0;
+  const size_t o_yrank = pos ? take((size_t)v.m * 4) : 0, o_xy = pos ? take((size_t)v.m * 8) : 0;
+  char* base = nullptr;
+  CK(cudaMallocAsync((void**)&base, off, c->stream));
+  v.arena = base;
+  v.raw = base + o_raw;
+  if (tcv) {
+    v.h16 = (__half*)(base + o_h16); v.nbh = (float*)(base + o_nbh); v.nrm = (float*)(base + o_nrm); v.aug16 = (__half*)(base + o_aug);
+    v.augq16 = (__half*)(base + o_augq); v.err = (float*)(base + o_err); v.stats = (uint32_t*)(base + o_stats);
   }
-  if (v.tc_capable()) {
-    v.m_pad = (v.m + tc::BN - 1) / tc::BN * tc::BN;
-    CK(cudaMallocAsync((void**)&v.h16, (size_t)v.m * 128 * 2, c->stream));
-    CK(cudaMallocAsync((void**)&v.nbh, (size_t)v.m_pad * 4, c->stream));
-    CK(cudaMallocAsync((void**)&v.nrm, (size_t)v.m_pad * 4, c->stream));
-    CK(cudaMallocAsync((void**)&v.aug16, (size_t)v.m_pad * 32, c->stream));
-    CK(cudaMallocAsync((void**)&v.augq16, (size_t)v.m_pad * 32, c->stream));
-    CK(cudaMallocAsync((void**)&v.err, (size_t)v.m_pad * 4, c->stream));
-    CK(cudaMallocAsync((void**)&v.stats, 16, c->stream));
-  }
+  if (pos) { v.d_yrank = (uint32_t*)(base + o_yrank); v.d_xy = (float*)(base + o_xy); }
   return B200M_OK;
 }
 static void free_view_buffers(b200m_ctx* c, ViewHost& v) {
-  if (v.raw) cudaFreeAsync(v.raw, c->stream);
-  if (v.h16) cudaFreeAsync(v.h16, c->stream);
-  if (v.nbh) cudaFreeAsync(v.nbh, c->stream);
-  if (v.nrm) cudaFreeAsync(v.nrm, c->stream);
-  if (v.aug16) cudaFreeAsync(v.aug16, c->stream);
-  if (v.augq16) cudaFreeAsync(v.augq16, c->stream);
-  if (v.err) cudaFreeAsync(v.err, c->stream);
-  if (v.stats) cudaFreeAsync(v.stats, c->stream);
-  if (v.d_xy) cudaFreeAsync(v.d_xy, c->stream);
-  if (v.d_yrank) cudaFreeAsync(v.d_yrank, c->stream);
+  if (v.arena) cudaFreeAsync(v.arena, c->stream);
+  if (v.raw_own) cudaFreeAsync(v.raw_own, c->stream);      // fp32 re-upload of a view whose uchar staging failed late
+  v.arena = nullptr; v.raw_own = nullptr;
   v.raw = nullptr; v.h16 = nullptr; v.nbh = nullptr; v.nrm = nullptr; v.aug16 = nullptr; v.d_xy = nullptr; v.d_yrank = nullptr;
   v.augq16 = nullptr; v.err = nullptr; v.stats = nullptr;
 }
@@ -351,11 +351,11 @@ static int make_view_dev(b200m_ctx* c, const ViewHost& v, ViewDev& d) {
   return B200M_OK;
 }
 
-static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag, cudaStream_t st) {
+static int run_prep(b200m_ctx* c, const ViewHost& v, uint32_t* d_flag, cudaStream_t st, bool zero_stats = true) {
   (void)c;
   if (!v.tc_capable()) return B200M_OK;
   const int grid = (v.m_pad + 7) / 8;
-  CK(cudaMemsetAsync(v.stats, 0, 16, st));
+  if (zero_stats) CK(cudaMemsetAsync(v.stats, 0, 16, st));
   if (v.store_dtype() == DT_F32) prep_view_kernel<float><<<grid, 256, 0, st>>>((const float*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16, v.augq16, v.err, v.stats);
   else prep_view_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)v.raw, v.m, v.h16, v.nbh, v.nrm, v.m_pad, d_flag, v.aug16, v.augq16, v.err, v.stats);
   CK(cudaGetLastError());
@@ -695,20 +695,24 @@ static int run_upload(b200m_ctx* c, const UploadJob& job) {
       const size_t fb = (size_t)v.m * v.dim * 4;
       CK(cudaMallocAsync(&nr, std::max<size_t>(fb, 256), c->up_stream));
       CK(cudaMemcpyAsync(nr, job.descs[i], fb, cudaMemcpyHostToDevice, c->up_stream));
-      CK(cudaFreeAsync(v.raw, c->up_stream));
-      v.raw = nr; v.stored_u8 = false;
+      v.raw = nr; v.raw_own = nr; v.stored_u8 = false;          // the uchar-sized region of the arena stays unused until the view goes
       int rc = make_view_dev(c, v, c->h_views[slot]);
       if (rc) return rc;
       CK(cudaMemcpyAsync(c->d_views + slot, c->h_views + slot, sizeof(ViewDev), cudaMemcpyHostToDevice, c->up_stream));
     }
     const bool flagged = v.tc_capable() || v.d_xy;
     if (flagged) CK(cudaMemsetAsync(c->d_flags + slot, 0, 4, c->up_stream));
+    {
+      // one memset for the per-view accumulators: stats (atomicMax) and, when the ranks are summed over several k ranges, yrank right behind
+      const bool rank_sums = v.d_xy && v.m > PR_KRANGE;
+      if (v.tc_capable()) CK(cudaMemsetAsync(v.stats, 0, rank_sums ? (size_t)((char*)v.d_yrank - (char*)v.stats) + (size_t)v.m * 4 : 16, c->up_stream));
+      else if (rank_sums) CK(cudaMemsetAsync(v.d_yrank, 0, (size_t)v.m * 4, c->up_stream));
+    }
     if (v.tc_capable()) {
-      int rc = run_prep(c, v, c->d_flags + slot, c->up_stream);
+      int rc = run_prep(c, v, c->d_flags + slot, c->up_stream, false);
       if (rc) return rc;
     }
     if (v.d_xy) {
-      CK(cudaMemsetAsync(v.d_yrank, 0, (size_t)v.m * 4, c->up_stream));
       pos_rank_kernel<<<dim3((v.m + PR_THREADS - 1) / PR_THREADS, (v.m + PR_KRANGE - 1) / PR_KRANGE), PR_THREADS, 0, c->up_stream>>>((const float2*)v.d_xy, v.m, v.d_yrank, c->d_flags + slot);
       CK(cudaGetLastError());
     }
@@ -839,6 +843,8 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
     if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return fail(B200M_ERR_ARG, "a view id appears twice in one upload call");
   }
   CK(cudaSetDevice(c->device));
+  const bool timing = getenv("B200M_TIMING") != nullptr;
+  const auto t_reg0 = std::chrono::steady_clock::now();
   int rc = wait_uploads(c);              // one job at a time: slot table, staging ring and view table are not shared between jobs
   if (rc) return rc;
   UploadJob job;
@@ -903,6 +909,8 @@ int b200m_upload_views_async(b200m_ctx* c, int n_views, const uint32_t* view_ids
     ++c->up_active;
   }
   c->up_cv.notify_all();
+  if (timing) fprintf(stderr, "[b200m] upload_views_async n=%d: registration (slots, allocations, tensor maps, table copies) %.2f ms\n", n_views,
+                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_reg0).count());
   return B200M_OK;
 }
 
@@ -924,13 +932,16 @@ int b200m_clear_views(b200m_ctx* c) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
   std::lock_guard<std::recursive_mutex> api_lock(c->api_mu);
   CK(cudaSetDevice(c->device));
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = wait_uploads(c);
   if (rc) return rc;
   c->pool->wait();
   CK(cudaStreamSynchronize(c->up_stream));
+  const size_t nv = c->views.size();
   for (auto& v : c->views) free_view_buffers(c, v);
   c->views.clear(); c->slot_of.clear(); c->free_slots.clear();
   CK(cudaStreamSynchronize(c->stream));
+  if (getenv("B200M_TIMING")) fprintf(stderr, "[b200m] clear_views n=%zu: %.2f ms\n", nv, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return B200M_OK;
 }
 
@@ -982,9 +993,10 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   const double t_begin = now();
 
   // PairSet semantics (types.hpp:23): unique, lexicographically ordered.
-  std::set<std::pair<uint32_t, uint32_t>> ps;
-  for (int k = 0; k < n_pairs; ++k) ps.insert({pairs[2 * k], pairs[2 * k + 1]});
-  std::vector<std::pair<uint32_t, uint32_t>> fwd(ps.begin(), ps.end());
+  std::vector<std::pair<uint32_t, uint32_t>> fwd((size_t)n_pairs);
+  for (int k = 0; k < n_pairs; ++k) fwd[k] = {pairs[2 * k], pairs[2 * k + 1]};
+  if (!std::is_sorted(fwd.begin(), fwd.end())) std::sort(fwd.begin(), fwd.end());
+  fwd.erase(std::unique(fwd.begin(), fwd.end()), fwd.end());
 
   const bool do_cross = cross != 0 && stage == B200M_STAGE_FULL;
   std::vector<Directed> dir;
@@ -1020,7 +1032,11 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   {
     std::vector<uint32_t> ord(fwd.size());
     for (size_t k = 0; k < fwd.size(); ++k) ord[k] = (uint32_t)k;
-    for (const Directed& d : dir) if (d.mode != PM_SKIP) pending |= !c->views[d.slot_i].ready || !c->views[d.slot_j].ready;
+    bool uploading;
+    { std::lock_guard<std::mutex> l(c->up_mu); uploading = c->up_active > 0; }
+    // arrival-order processing with short first batches only while copies are really in flight (not for views that are merely not yet
+    // marked ready after a completed upload)
+    if (uploading) for (const Directed& d : dir) if (d.mode != PM_SKIP) pending |= !c->views[d.slot_i].ready || !c->views[d.slot_j].ready;
     if (pending) {
       std::vector<uint64_t> key(fwd.size());
       for (size_t k = 0; k < fwd.size(); ++k) key[k] = std::max(c->views[dir[k * step].slot_i].seq, c->views[dir[k * step].slot_j].seq);

@@ -35,7 +35,8 @@ pos_rank_kernel(const float2* __restrict__ xy, int m, uint32_t* __restrict__ yra
     dup |= (k != i) && (o.x == me.x || o.y == me.y);
   }
   if (i < m) {
-    if (less) atomicAdd(&yrank[i], less);
+    if (gridDim.y == 1) yrank[i] = less;                 // one k range: the count is complete (the caller did not zero yrank)
+    else if (less) atomicAdd(&yrank[i], less);
     if (dup || (blockIdx.y == 0 && (me.x != me.x || me.y != me.y))) atomicOr(flags, VF_POS_NONGENERIC);
   }
 }

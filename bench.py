@@ -349,7 +349,12 @@ def main():
         # one engine process per GPU shares the host: stay on the GPU's NUMA node, split the cores between the ranks' pools and
         # keep fewer staging copies in flight per rank (profiles/r01d_multi_rank_host_settings.md)
         numa = pin_to_gpu_numa_node(local)
-        os.environ.setdefault("B200M_HOST_THREADS", str(max(6, host_cores() // world)))
+        # threads of this rank's staging / finishing pool: the CPUs it may use (after the pinning: one NUMA node) shared with the other
+        # ranks on the same node, capped by the container's CPU quota split over all ranks
+        sharing = max(1, world // 2) if numa.startswith("node") else world
+        q = cgroup_cpu_quota()
+        per_rank = min(len(os.sched_getaffinity(0)) // sharing, int(q // world) if q else 1 << 30)
+        os.environ.setdefault("B200M_HOST_THREADS", str(max(6, min(32, per_rank))))
         os.environ.setdefault("B200M_UP_LAG", "6")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
