@@ -52,13 +52,17 @@ enum : int { MODE_MATCH = 0, MODE_KNN = 1, MODE_REAL = 2 };
 // h = ||b||^2/2 - a.b directly.  That removes the half-norm ring, 32 LDS.128 and 64 FADD2 per thread and tile from
 // the epilogue for 12.5 % more tensor work.
 template <bool AUG, bool REAL = false> struct Lay {
-  static constexpr int NS = AUG ? 3 : 4;                             // database smem stages per CTA
+  // database smem stages per CTA.  r02: a 4th stage for the AUG layout (one more tile of TMA lead: 3717 instead of 2347 cycles between a box
+  // being issued and its use) changed neither the per-tile period nor the bench value - the feed is not the limit - so the AUG kernels keep
+  // 3 stages and leave the shared memory to L1 (the re-scoring warps' row loads) and to the upload-stream kernels that co-run.
+  static constexpr int NS = AUG ? 3 : 4;
+  static constexpr int MRG_GROUPS = AUG ? 1 : 3;                     // column groups merged through shared memory (8 epilogue warps: 1; the 16-warp variant: 3)
   static constexpr int STAGE = DBH_BYTES + (AUG ? AUG_BYTES : 0);
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_DB = OFF_Q + 2 * Q_BYTES;
   static constexpr int OFF_NB = OFF_DB + NS * STAGE;                 // non-AUG: half-norm ring; AUG: the constant A tile (4 KB); REAL: the query's own limb tile, 2 buffers
   static constexpr int OFF_MRG = OFF_NB + (AUG ? (REAL ? 2 : 1) * AUG_BYTES : NS * NB_BYTES);
-  static constexpr int OFF_VQ = OFF_MRG + 2 * 3 * BM * 16;           // candidate queue: 2 buffers x 128 Cand (32 slots per epilogue quadrant)
+  static constexpr int OFF_VQ = OFF_MRG + 2 * MRG_GROUPS * BM * 16;  // candidate queue: 2 buffers x 128 Cand (32 slots per epilogue quadrant)
   static constexpr int OFF_VQX = OFF_VQ + 2 * BM * 16;               // REAL: 5th word of the queued candidates (p4), 2 x 128 x 4 B
   static constexpr int OFF_VQN = OFF_VQX + (REAL ? 2 * BM * 4 : 0);  // 2 x (4 per-quadrant counts + pair index), 32 B each
   static constexpr int OFF_BAR = OFF_VQN + 2 * 32;
@@ -225,7 +229,10 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         ptx::mbar_wait(&q_full[qb], qph);
         bool db_ready = false, tm_ready = false;   // barriers of the coming tile already observed
         for (int t = 0; t < ntiles; ++t) {
+          if (trace != nullptr && tt < ptx::TRACE_TILES) trace[((size_t)0 * ptx::TRACE_TILES + tt) * 4 + 2] = (db_ready ? 1 : 0) | (tm_ready ? 2 : 0);   // debug: did the look-ahead polls succeed
+          ptx::trace_stamp(trace, 1, tt, 0);
           if (!db_ready) ptx::mbar_wait(&db_full[st], sph);
+          ptx::trace_stamp(trace, 1, tt, 3);
           if (!tm_ready) ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
           ptx::trace_stamp(trace, 1, tt, 1);
           ptx::tc_fence_after();
@@ -244,10 +251,16 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
             ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32),
                                  ptx::umma_desc_k_sw128(b_base + (k >> 2) * (128 * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u);
             if (k == 3 && more) db_ready = ptx::mbar_try_wait(&db_full[nst], nsph);
-            if (k == (AUG ? 6 : 5) && more) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+            // r02 trace (tools/gpu_trace.py): the MMA queue is only ~1-2 instructions deep, so the issuer runs about one MMA ahead of the
+            // tensor pipe and ANY stall of more than ~150 cycles after the commit becomes a pipe bubble (gap 304 + issue 1039 = 1344 cycles
+            // per 1152-cycle tile).  The other TMEM stage is handed back ~650 cycles after the previous tile completed, i.e. while MMA 5-6 of
+            // this tile execute: a poll after the 7th MMA failed by a hair every tile; after the 8th (and once more after the 9th) it succeeds.
+            if (k == (AUG ? 7 : 6) && more) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
           }
-          if (AUG)   // 9th K-step: constants x half-norm limbs
+          if (AUG) {  // 9th K-step: constants x half-norm limbs
             ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB) + (REAL ? qb * AUG_BYTES : 0)), ptx::umma_desc_k_sw32(b_base + DBH_BYTES), idesc, 1u);
+            if (more && !tm_ready) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+          }
           ptx::umma_commit_2sm_mc(&db_empty[st], 3);
           ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
           ptx::trace_stamp(trace, 1, tt, 2); ++tt;
@@ -369,7 +382,7 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
         if (!AUG && t + 1 < ntiles) ptx::mbar_wait(&nb_full[st], sph);
       }
       // merge the column groups of each query row, pre-test, emit candidates
-      float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * 3 * BM;
+      float4* mrg = reinterpret_cast<float4*>(smem + OFF_MRG) + par * L::MRG_GROUPS * BM;
       if (colq > 0) {
         if (REAL) mrg[(colq - 1) * BM + row] = make_float4(__uint_as_float(s4.p1), __uint_as_float(s4.p2), __uint_as_float(s4.p3), __uint_as_float(s4.p4));
         else if (KNN) mrg[(colq - 1) * BM + row] = make_float4(sk.m1, sk.m2, __uint_as_float(sk.g1), __uint_as_float(sk.g2));

@@ -23,6 +23,10 @@ lo, hi = 64, 192     # steady-state tiles
 print("per-tile period (MMA commit issued -> next):", np.diff(mma[lo:hi, 2]).mean())
 print("MMA: barriers ready -> commit issued (issue loop incl. next-tile polls):", (mma[lo:hi, 2] - mma[lo:hi, 1]).mean())
 print("MMA: commit issued(t-1) -> barriers ready(t) (gap):", (mma[lo + 1:hi, 1] - mma[lo:hi - 1, 2]).mean())
+print("MMA: loop top -> db_full observed:", (mma[lo:hi, 3] - mma[lo:hi, 0]).mean(), " db_full -> tm_empty observed:", (mma[lo:hi, 1] - mma[lo:hi, 3]).mean(),
+      " commit issued(t-1) -> loop top(t):", (mma[lo + 1:hi, 0] - mma[lo:hi - 1, 2]).mean())
+flags = prod[lo:hi, 2]
+print("look-ahead polls: db_full ready %.0f %%, tm_empty ready %.0f %%" % (100 * (flags & 1).mean(), 100 * ((flags >> 1) & 1).mean()))
 print("producer: slot free -> issued:", (prod[lo:hi, 1] - prod[lo:hi, 0]).mean(), " period:", np.diff(prod[lo:hi, 0]).mean())
 for name, e in (("epi half0", e0), ("epi half1", e1)):
     print(f"{name}: wait tm_full: {(e[lo:hi, 1] - e[lo:hi, 0]).mean():.0f}  process: {(e[lo:hi, 2] - e[lo:hi, 1]).mean():.0f}  period: {np.diff(e[lo:hi, 2]).mean():.0f}")
