@@ -243,9 +243,10 @@ rescore_real_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict
 
 // Fallback of the real-valued path, per pair: the flagged queries of one pair (a few; FB_PER_PAIR at most here) against the whole database
 // image in the reference's arithmetic.  One block per (pair, group of XP_MAXQ queries); the database rows stream through shared memory in coalesced 64-row tiles
-// (read ONCE per group of XR_MAXQ queries); thread (r, l) owns SSE lane l of tile row r: s_l += (q - row)^2 over components l, l+4, ...
+// (read once per group); thread (r, l) owns SSE lane l of tile row r: s_l += (q - row)^2 over components l, l+4, ...
 // in order, the four lanes of a row combined as ((s0+s1)+s2)+s3 (feature/metric.hpp:100-116).
-constexpr int XP_THREADS = 256, XP_ROWS = 64, XP_LD = 132, XP_MAXQ = 8;
+constexpr int XP_THREADS = 256, XP_ROWS = 64, XP_LD = 132, XP_MAXQ = 2;   // 2 queries per block: their components live in REGISTERS (the inner
+                                                                          // loop of the 8-query version read them from shared memory and was LDS-bound)
 __global__ void __launch_bounds__(XP_THREADS)
 exact_rows_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint4* __restrict__ pair_list, const int* __restrict__ pair_cnt,
                         Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
@@ -264,7 +265,14 @@ exact_rows_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __rest
     const int e0 = blockIdx.y * XP_MAXQ;
     if (e0 >= n_all) return;
     const int ne = min(XP_MAXQ, n_all - e0);
-    for (int k = tid; k < ne * 128; k += XP_THREADS) qs[k] = view_elem(vj, (size_t)pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + (k >> 7)].y * 128 + (k & 127));
+    for (int k = tid; k < XP_MAXQ * 128; k += XP_THREADS)
+      qs[k] = (k >> 7) < ne ? view_elem(vj, (size_t)pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + (k >> 7)].y * 128 + (k & 127)) : 0.f;
+    __syncthreads();
+    float qr[XP_MAXQ][32];                                   // this thread's SSE lane of every query: components l, l + 4, ...
+#pragma unroll
+    for (int e = 0; e < XP_MAXQ; ++e)
+#pragma unroll
+      for (int t = 0; t < 32; ++t) qr[e][t] = qs[e * 128 + 4 * t + l];
     float m1[XP_MAXQ], m2[XP_MAXQ]; uint32_t i1[XP_MAXQ];
 #pragma unroll
     for (int e = 0; e < XP_MAXQ; ++e) { m1[e] = INFINITY; m2[e] = INFINITY; i1[e] = 0xFFFFFFFFu; }
@@ -284,13 +292,11 @@ exact_rows_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __rest
       float s[XP_MAXQ];
 #pragma unroll
       for (int e = 0; e < XP_MAXQ; ++e) s[e] = 0.f;
-#pragma unroll 4
+#pragma unroll
       for (int t = 0; t < 32; ++t) {
         const float tv = tile[r * XP_LD + 4 * t + l];
 #pragma unroll
-        for (int e = 0; e < XP_MAXQ; ++e) {
-          if (e < ne) { const float d = __fsub_rn(qs[e * 128 + 4 * t + l], tv); s[e] = __fadd_rn(s[e], __fmul_rn(d, d)); }
-        }
+        for (int e = 0; e < XP_MAXQ; ++e) { const float d = __fsub_rn(qr[e][t], tv); s[e] = __fadd_rn(s[e], __fmul_rn(d, d)); }   // an unused query slot holds zeros
       }
       const uint32_t row = row0 + r;
 #pragma unroll
