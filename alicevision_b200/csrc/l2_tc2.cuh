@@ -217,56 +217,63 @@ l2_top2_tc2_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs this loop converged and only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
+    // r02 (profiles/r02_k1_issue_bound.md): with `if (lane == 0)` around the loop the compiler kept the shared-memory descriptors in vector
+    // registers of a divergent thread - ~17 dependent ALU / R2UR instructions in front of every UTCHMMA, ~1040 cycles of issue per
+    // 1152-cycle tile: the kernel was bound by this thread, not by the tensor pipe.  Warp-uniform control flow lets the descriptor
+    // arithmetic live in the uniform datapath.
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN, false, true);   // M=256 across the pair, D = A * (-B)^T
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t db_addr = ptx::smem_u32(smem + OFF_DB);
+      const bool issuer = ptx::elect_one();
+      long long* mtrace = issuer ? trace : nullptr;
       uint32_t qb = 0, qph = 0, st = 0, sph = 0, ac = 0, aph = 0, tt = 0;
       for (int it = cluster_id; it < n_items; it += n_clusters) {
         const WorkItem w = items[it];
         const PairDev p = pairs[w.pair];
         const int ntiles = ((int)p.m_i + BN - 1) / BN;
         ptx::mbar_wait(&q_full[qb], qph);
-        bool db_ready = false, tm_ready = false;   // barriers of the coming tile already observed
+        bool db_ready = false, tm_ready = false;   // barriers of the coming tile already observed (warp-uniform)
         for (int t = 0; t < ntiles; ++t) {
-          if (trace != nullptr && tt < ptx::TRACE_TILES) trace[((size_t)0 * ptx::TRACE_TILES + tt) * 4 + 2] = (db_ready ? 1 : 0) | (tm_ready ? 2 : 0);   // debug: did the look-ahead polls succeed
-          ptx::trace_stamp(trace, 1, tt, 0);
+          if (mtrace != nullptr) {     // debug only (CTA 0 with tracing on): did the look-ahead polls succeed; loop-top time
+            if (tt < ptx::TRACE_TILES) mtrace[((size_t)0 * ptx::TRACE_TILES + tt) * 4 + 2] = (db_ready ? 1 : 0) | (tm_ready ? 2 : 0);
+            ptx::trace_stamp(mtrace, 1, tt, 0);
+          }
           if (!db_ready) ptx::mbar_wait(&db_full[st], sph);
-          ptx::trace_stamp(trace, 1, tt, 3);
           if (!tm_ready) ptx::mbar_wait(&tm_empty[ac], aph ^ 1);
-          ptx::trace_stamp(trace, 1, tt, 1);
+          ptx::trace_stamp(mtrace, 1, tt, 1);
           ptx::tc_fence_after();
           const uint32_t a_base = q_addr + qb * Q_BYTES, b_base = db_addr + st * STAGE, d_addr = tmem_base + ac * BN;
-          // Observing a completed mbarrier costs ~100 cycles; doing that between the commit of one tile and the first MMA of
-          // the next would idle the tensor pipe.  So the NEXT tile's barriers are polled while this tile's MMAs are queued:
-          // the database slot (full long ago) after the 4th MMA, the TMEM stage (drained by the epilogue ~0.8 tile after its
-          // MMAs retired) as late as possible, before the last two MMAs.  A failed poll falls back to a blocking wait at
-          // the top of the next tile.
+          // The NEXT tile's barriers are polled while this tile's MMAs are queued (the database slot after the 4th MMA, the TMEM stage
+          // before the last two); a failed poll falls back to a blocking wait at the top of the next tile.
           const uint32_t nst = (st + 1 == NS) ? 0 : st + 1, nsph = (st + 1 == NS) ? (sph ^ 1) : sph;
           const uint32_t nac = ac ^ 1, naph = (nac == 0) ? (aph ^ 1) : aph;
           const bool more = (t + 1 < ntiles);
           db_ready = tm_ready = false;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw128(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32),
-                                 ptx::umma_desc_k_sw128(b_base + (k >> 2) * (128 * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u);
-            if (k == 3 && more) db_ready = ptx::mbar_try_wait(&db_full[nst], nsph);
-            // r02 trace (tools/gpu_trace.py): the MMA queue is only ~1-2 instructions deep, so the issuer runs about one MMA ahead of the
-            // tensor pipe and ANY stall of more than ~150 cycles after the commit becomes a pipe bubble (gap 304 + issue 1039 = 1344 cycles
-            // per 1152-cycle tile).  The other TMEM stage is handed back ~650 cycles after the previous tile completed, i.e. while MMA 5-6 of
-            // this tile execute: a poll after the 7th MMA failed by a hair every tile; after the 8th (and once more after the 9th) it succeeds.
-            if (k == (AUG ? 7 : 6) && more) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+            const uint64_t da = ptx::umma_desc_k_sw128(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
+            const uint64_t db = ptx::umma_desc_k_sw128(b_base + (k >> 2) * (128 * 128) + (k & 3) * 32);
+            if (issuer) ptx::umma_f16_ss_2sm(d_addr, da, db, idesc, k > 0 ? 1u : 0u);
+            if (k == 3 && more) db_ready = __all_sync(0xffffffffu, ptx::mbar_try_wait(&db_full[nst], nsph));
+            if (k == (AUG ? 6 : 5) && more) tm_ready = __all_sync(0xffffffffu, ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1));
           }
           if (AUG) {  // 9th K-step: constants x half-norm limbs
-            ptx::umma_f16_ss_2sm(d_addr, ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB) + (REAL ? qb * AUG_BYTES : 0)), ptx::umma_desc_k_sw32(b_base + DBH_BYTES), idesc, 1u);
-            if (more && !tm_ready) tm_ready = ptx::mbar_try_wait(&tm_empty[nac], naph ^ 1);
+            const uint64_t da = ptx::umma_desc_k_sw32(ptx::smem_u32(smem + OFF_NB) + (REAL ? qb * AUG_BYTES : 0));
+            const uint64_t db = ptx::umma_desc_k_sw32(b_base + DBH_BYTES);
+            if (issuer) ptx::umma_f16_ss_2sm(d_addr, da, db, idesc, 1u);
           }
-          ptx::umma_commit_2sm_mc(&db_empty[st], 3);
-          ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
-          ptx::trace_stamp(trace, 1, tt, 2); ++tt;
+          if (issuer) {
+            ptx::umma_commit_2sm_mc(&db_empty[st], 3);
+            ptx::umma_commit_2sm_mc(&tm_full[ac], 3);
+          }
+          __syncwarp();
+          ptx::trace_stamp(mtrace, 1, tt, 2); ++tt;
           st = nst; sph = nsph; ac = nac; aph = naph;
         }
-        ptx::umma_commit_2sm_mc(&q_empty[qb], 3);
+        if (issuer) ptx::umma_commit_2sm_mc(&q_empty[qb], 3);
+        __syncwarp();
         qb ^= 1; if (qb == 0) qph ^= 1;
       }
     }

@@ -23,8 +23,7 @@ lo, hi = 64, 192     # steady-state tiles
 print("per-tile period (MMA commit issued -> next):", np.diff(mma[lo:hi, 2]).mean())
 print("MMA: barriers ready -> commit issued (issue loop incl. next-tile polls):", (mma[lo:hi, 2] - mma[lo:hi, 1]).mean())
 print("MMA: commit issued(t-1) -> barriers ready(t) (gap):", (mma[lo + 1:hi, 1] - mma[lo:hi - 1, 2]).mean())
-print("MMA: loop top -> db_full observed:", (mma[lo:hi, 3] - mma[lo:hi, 0]).mean(), " db_full -> tm_empty observed:", (mma[lo:hi, 1] - mma[lo:hi, 3]).mean(),
-      " commit issued(t-1) -> loop top(t):", (mma[lo + 1:hi, 0] - mma[lo:hi - 1, 2]).mean())
+print("MMA: loop top -> barriers observed:", (mma[lo:hi, 1] - mma[lo:hi, 0]).mean(), " commit issued(t-1) -> loop top(t):", (mma[lo + 1:hi, 0] - mma[lo:hi - 1, 2]).mean())
 flags = prod[lo:hi, 2]
 print("look-ahead polls: db_full ready %.0f %%, tm_empty ready %.0f %%" % (100 * (flags & 1).mean(), 100 * ((flags >> 1) & 1).mean()))
 print("producer: slot free -> issued:", (prod[lo:hi, 1] - prod[lo:hi, 0]).mean(), " period:", np.diff(prod[lo:hi, 0]).mean())
