@@ -456,7 +456,7 @@ def main():
                                "traffic_note": tr["note"] if tr else None, "kernel": "hamming_top2_kernel", "kernel_ms_per_step": ms_search,
                                "note": "integer-ALU bound by construction (M^2 x (16 XOR + 22 LOP3 + 5 POPC) per pair vs 2*M*64 bytes); HBM fraction reported because the north star asks"}
         else:
-            tr = ncu_traffic("l2_top2_tc2_kernel") if (args.tc_variant == 4 and M == 8192 and tc_pairs > 0) else None
+            tr = (ncu_traffic("l2_top2_tc2_kernel") if tc_pairs > 0 else ncu_traffic("l2_top2_tc2_kernel_real") if real_pairs > 0 else None) if (args.tc_variant == 4 and M == 8192) else None
             kern = {1: "tc::l2_top2_tc_kernel", 2: "tc2::l2_top2_tc2_kernel<8,false> (cta_group::2)", 3: "tc2::l2_top2_tc2_kernel<16,false> (cta_group::2)",
                     4: "tc2::l2_top2_tc2_kernel<8,true> (cta_group::2, K=128+16)"}[args.tc_variant] if tc_pairs > 0 else (
                         "tc2::l2_top2_tc2_kernel<8,true,MODE_REAL> (cta_group::2, fp16-rounded filter GEMM, K=128+16) + exact re-scoring in the reference's fp32 order + exact_rows fallback"
