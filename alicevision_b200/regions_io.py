@@ -189,3 +189,66 @@ def filterMatchesByDesc(allMatches: PairwiseMatches, descTypesFilter) -> None:
             allMatches[k] = kept
         else:
             del allMatches[k]
+
+
+# ---- regions of a set of views (sfm/pipeline/regionsIO.cpp:25-78,197-251) ------------------------------------------------
+# imageDescriberType name (feature/imageDescriberCommon.cpp:46-90) -> (element type, descriptor length, binary), i.e. the Regions class its
+# ImageDescriber allocates (feature/regionsFactory.hpp:15-33)
+DESCRIBER_REGIONS = {
+    "sift": (np.uint8, 128, False), "sift_upright": (np.uint8, 128, False), "dspsift": (np.uint8, 128, False), "sift_ocv": (np.uint8, 128, False),
+    "sift_float": (np.float32, 128, False),
+    "akaze": (np.float32, 64, False), "akaze_ocv": (np.float32, 64, False), "akaze_liop": (np.uint8, 144, False), "akaze_mldb": (np.uint8, 64, True),
+    "cctag3": (np.uint8, 128, False), "cctag4": (np.uint8, 128, False), "tag16h5": (np.uint8, 150, False),
+}
+
+
+def loadRegions(folders, viewId: int, imageDescriberType: str):
+    """sfm::loadRegions (regionsIO.cpp:25-78): ``<viewId>.<describerType>.feat`` / ``.desc`` from the LAST folder that holds both; raises like the
+    reference when no folder does or a file is invalid.  Returns ``matching.Regions`` (descriptors, positions, binary flag) with the full
+    features[n, 4] kept as ``.features``."""
+    from .matching import Regions
+    if imageDescriberType not in DESCRIBER_REGIONS:
+        raise ValueError(f"unknown image describer type '{imageDescriberType}'")
+    dtype, dim, binary = DESCRIBER_REGIONS[imageDescriberType]
+    base = f"{int(viewId)}.{imageDescriberType}"
+    feat = desc = None
+    for folder in folders:
+        f, d = os.path.join(folder, base + ".feat"), os.path.join(folder, base + ".desc")
+        if os.path.exists(f) and os.path.exists(d):
+            feat, desc = f, d
+    if feat is None:
+        raise IOError(f"Can't find view {int(viewId)} region files in folders {', '.join(folders)}")
+    feats = loadFeatsFromFile(feat)
+    descs = loadDescsFromBinFile(desc, dim, dtype)
+    if len(feats) != len(descs):
+        raise IOError(f"Invalid {imageDescriberType} regions files for the view {int(viewId)}: {len(feats)} features, {len(descs)} descriptors")
+    r = Regions(descs, feats[:, :2], binary=binary)
+    r.features = feats
+    return r
+
+
+def loadRegionsPerView(viewIds, folders, imageDescriberTypes, viewIdFilter=None, threads: int = 8):
+    """sfm::loadRegionsPerView (regionsIO.cpp:197-251) without the SfMData container: ``viewIds`` are the views of the scene, ``folders`` the
+    features folders (sfmData's first, then the user's, as the caller concatenates them).  Returns ``(ok, {viewId: {describerType: Regions}})``;
+    ok is False as soon as one view cannot be loaded (the reference logs the error and returns false).  Files are read in parallel
+    (the reference uses 3 OpenMP threads; the parsing is the C library's and releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    folders = list(dict.fromkeys(folders))                       # std::unique on the concatenated list
+    wanted = [int(v) for v in viewIds if viewIdFilter is None or len(viewIdFilter) == 0 or int(v) in viewIdFilter]
+    jobs = [(v, t) for v in wanted for t in imageDescriberTypes]
+    out: Dict[int, Dict[str, object]] = {}
+    ok = True
+
+    def one(job):
+        try:
+            return job, loadRegions(folders, job[0], job[1]), None
+        except Exception as e:      # noqa: BLE001
+            return job, None, e
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        for (v, t), r, err in ex.map(one, jobs):
+            if err is not None:
+                ok = False
+                continue
+            out.setdefault(v, {})[t] = r
+    return ok, out

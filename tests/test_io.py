@@ -195,3 +195,54 @@ def test_corrupt_matches_file_is_an_error_not_an_allocation(tmp_path):
     cut.write_text("0 1\n1\nsift 3\n1 2\n3 4\n")           # announces 3 matches, holds 2
     with pytest.raises(IOError, match="truncated"):
         rio.LoadMatchFile({}, str(cut))
+
+
+# ---- sfm::loadRegions / loadRegionsPerView (sfm/pipeline/regionsIO.cpp:25-78,197-251) ------------------------------------
+def test_loadRegionsPerView_from_files_written_by_the_reference(tmp_path):
+    """<viewId>.<describerType>.feat/.desc files written by the (compiled) reference's Regions::Save in two folders: loadRegionsPerView returns
+    the reference's regions for every (view, type); the last folder holding both files wins; a view without files makes the call fail like the
+    reference (false) while the others are still loaded; the view filter restricts what is read."""
+    ora = oracle.best()
+    a, b = tmp_path / "feats_a", tmp_path / "feats_b"
+    a.mkdir(); b.mkdir()
+    sift, _ = synth.sift_images(3, 200, np.uint8, seed=7, pool_factor=1.0)
+    fsift = [d.astype(np.float32) + 0.5 for d in sift]
+    mldb, _ = synth.mldb_images(2, 150, seed=7)
+    written = {}
+    for v, d in zip((11, 12, 4000000000), sift):
+        f = _feats(len(d), v % 97)
+        ora.save_regions(d, f, str(a / f"{v}.sift.feat"), str(a / f"{v}.sift.desc"))
+        written[(v, "sift")] = (d, f)
+    for v, d in zip((11, 12), fsift):
+        f = _feats(len(d), v + 1)
+        ora.save_regions(d, f, str(b / f"{v}.sift_float.feat"), str(b / f"{v}.sift_float.desc"))
+        written[(v, "sift_float")] = (d, f)
+    for v, d in zip((11, 12), mldb):
+        f = _feats(len(d), v + 2)
+        ora.save_regions(d, f, str(b / f"{v}.akaze_mldb.feat"), str(b / f"{v}.akaze_mldb.desc"), binary=True)
+        written[(v, "akaze_mldb")] = (d, f)
+    # view 12 "sift" exists in both folders with different content: the LAST folder wins (regionsIO.cpp:36-46 keeps overwriting)
+    other = sift[0][::-1].copy(); fo = _feats(len(other), 5)
+    ora.save_regions(other, fo, str(b / "12.sift.feat"), str(b / "12.sift.desc"))
+    written[(12, "sift")] = (other, fo)
+    ok, rpv = rio.loadRegionsPerView([11, 12], [str(a), str(b), str(b)], ["sift", "sift_float", "akaze_mldb"])
+    assert ok and sorted(rpv) == [11, 12]
+    for (v, t), (d, f) in written.items():
+        if v not in rpv:
+            continue
+        r = rpv[v][t]
+        assert np.array_equal(r.descriptors, d) and r.descriptors.dtype == d.dtype and r.IsBinary() == (t == "akaze_mldb")
+        folder = b if (b / f"{v}.{t}.feat").exists() else a                # the text format keeps 6 significant digits: compare with the reference's READER
+        rd, rf = ora.load_regions(str(folder / f"{v}.{t}.feat"), str(folder / f"{v}.{t}.desc"), d.dtype, d.shape[1], binary=t == "akaze_mldb")
+        assert np.array_equal(r.descriptors, rd) and np.array_equal(r.features, rf) and np.array_equal(r.positions, rf[:, :2])
+        assert np.allclose(r.features, f, rtol=1e-5, atol=1e-6)
+    ok, rpv = rio.loadRegionsPerView([11, 12, 4000000000], [str(a), str(b)], ["sift"], viewIdFilter={4000000000})
+    assert ok and list(rpv) == [4000000000] and np.array_equal(rpv[4000000000]["sift"].descriptors, sift[2])
+    ok, rpv = rio.loadRegionsPerView([11, 99], [str(a)], ["sift"])          # view 99 has no files
+    assert not ok and list(rpv) == [11]
+    with pytest.raises(IOError, match="Can't find view 99"):
+        rio.loadRegions([str(a)], 99, "sift")
+    (a / "13.sift.feat").write_text("1 2 3 4\n")                            # 1 feature, 0 descriptors
+    rio.saveDescsToBinFile(str(a / "13.sift.desc"), np.zeros((0, 128), np.uint8))
+    with pytest.raises(IOError, match="Invalid sift regions files"):
+        rio.loadRegions([str(a)], 13, "sift")
