@@ -435,6 +435,7 @@ static int ensure_batch_buffers(b200m_ctx* c) {
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<false>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true, true>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc2::l2_top2_tc2_kernel<8, true, tc2::MODE_KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Lay<true>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(exact_rows_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XP_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
   CK(cudaFuncSetAttribute(exact_top2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM));
@@ -1173,7 +1174,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
         rescore_real_kernel<<<dim3(np, 4), VERIFY_WARPS_REAL * 32, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_cands, bb.d_candx, bb.d_count, ratio_sq, c->d_err, fbs);
         ++launches;
       }
-      exact_rows_pairs_kernel<<<dim3(np, FB_PER_PAIR / XP_MAXQ), XP_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb_pair, bb.d_fb_pair_cnt, bb.d_cands, bb.d_count, ratio_sq);
+      exact_rows_pairs_kernel<<<dim3(np, FB_PER_PAIR / XP_MAXQ), XP_THREADS, XP_SMEM, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb_pair, bb.d_fb_pair_cnt, bb.d_cands, bb.d_count, ratio_sq);
       exact_rows_kernel<<<c->num_sms, XR_THREADS, 0, c->stream>>>(c->d_views, bb.d_pairs, bb.d_fb, bb.d_fb_count, (int)CAND_CAP, bb.d_cands, bb.d_count, ratio_sq);   // overflow list: normally empty
       launches += 2;
     }

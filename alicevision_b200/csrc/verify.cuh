@@ -245,98 +245,116 @@ rescore_real_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict
 // image in the reference's arithmetic.  One block per (pair, group of XP_MAXQ queries); the database rows stream through shared memory in coalesced 64-row tiles
 // (read once per group); thread (r, l) owns SSE lane l of tile row r: s_l += (q - row)^2 over components l, l+4, ...
 // in order, the four lanes of a row combined as ((s0+s1)+s2)+s3 (feature/metric.hpp:100-116).
-constexpr int XP_THREADS = 256, XP_ROWS = 64, XP_LD = 132, XP_MAXQ = 2;   // 2 queries per block: their components live in REGISTERS (the inner
-                                                                          // loop of the 8-query version read them from shared memory and was LDS-bound)
+constexpr int XP_THREADS = 256, XP_ROWS = 64, XP_LD = 132, XP_MAXQ = 4;   // 4 queries per block: their components live in REGISTERS (with 8
+// queries in shared memory the inner loop was LDS-bound; with 2 the database image was re-read too often: 26.8 % of the device time of the
+// real-valued bench).  The tiles are double-buffered with cp.async so that a block streams its 4 MB image without stalling on every tile.
+constexpr int XP_TILE_BYTES = XP_ROWS * XP_LD * 4;
+constexpr int XP_SMEM = 2 * XP_TILE_BYTES;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int n = valid ? 16 : 0;                                   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(XP_THREADS)
 exact_rows_pairs_kernel(const ViewDev* __restrict__ views, const PairDev* __restrict__ pairs, const uint4* __restrict__ pair_list, const int* __restrict__ pair_cnt,
                         Cand* __restrict__ cands, int* __restrict__ cand_count, float ratio_sq) {
   const PairDev p = pairs[blockIdx.x];
   if (p.mode != PM_TC_REAL) return;
   const int n_all = min(pair_cnt[blockIdx.x], FB_PER_PAIR);
-  if (n_all == 0) return;
-  __shared__ float tile[XP_ROWS * XP_LD];
+  const int e0 = blockIdx.y * XP_MAXQ;                      // grid.y = FB_PER_PAIR / XP_MAXQ: one block per group of XP_MAXQ flagged queries of the pair
+  if (e0 >= n_all) return;
+  const int ne = min(XP_MAXQ, n_all - e0);
+  extern __shared__ __align__(16) float xp_tiles[];         // 2 x [XP_ROWS][XP_LD]
   __shared__ float qs[XP_MAXQ * 128];
   __shared__ float rm1[XP_MAXQ][XP_THREADS / 32], rm2[XP_MAXQ][XP_THREADS / 32];
   __shared__ uint32_t ri1[XP_MAXQ][XP_THREADS / 32];
   const ViewDev& vi = views[p.view_i]; const ViewDev& vj = views[p.view_j];
   const int tid = threadIdx.x, r = tid >> 2, l = tid & 3, lane = tid & 31, warp = tid >> 5;
   const unsigned gmask = 0xFu << (lane & ~3);
-  {                                          // grid.y = FB_PER_PAIR / XP_MAXQ: one block per group of XP_MAXQ flagged queries of the pair
-    const int e0 = blockIdx.y * XP_MAXQ;
-    if (e0 >= n_all) return;
-    const int ne = min(XP_MAXQ, n_all - e0);
-    for (int k = tid; k < XP_MAXQ * 128; k += XP_THREADS)
-      qs[k] = (k >> 7) < ne ? view_elem(vj, (size_t)pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + (k >> 7)].y * 128 + (k & 127)) : 0.f;
-    __syncthreads();
-    float qr[XP_MAXQ][32];                                   // this thread's SSE lane of every query: components l, l + 4, ...
+  for (int k = tid; k < XP_MAXQ * 128; k += XP_THREADS)
+    qs[k] = (k >> 7) < ne ? view_elem(vj, (size_t)pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + (k >> 7)].y * 128 + (k & 127)) : 0.f;
+  __syncthreads();
+  float qr[XP_MAXQ][32];                                    // this thread's SSE lane of every query: components l, l + 4, ...
 #pragma unroll
-    for (int e = 0; e < XP_MAXQ; ++e)
+  for (int e = 0; e < XP_MAXQ; ++e)
 #pragma unroll
-      for (int t = 0; t < 32; ++t) qr[e][t] = qs[e * 128 + 4 * t + l];
-    float m1[XP_MAXQ], m2[XP_MAXQ]; uint32_t i1[XP_MAXQ];
+    for (int t = 0; t < 32; ++t) qr[e][t] = qs[e * 128 + 4 * t + l];
+  float m1[XP_MAXQ], m2[XP_MAXQ]; uint32_t i1[XP_MAXQ];
 #pragma unroll
-    for (int e = 0; e < XP_MAXQ; ++e) { m1[e] = INFINITY; m2[e] = INFINITY; i1[e] = 0xFFFFFFFFu; }
-    for (uint32_t row0 = 0; row0 < p.m_i; row0 += XP_ROWS) {
-      __syncthreads();
-      for (int k = tid; k < XP_ROWS * 32; k += XP_THREADS) {          // 64 rows x 32 float4, coalesced
-        const int rr = k >> 5, c4 = k & 31;
+  for (int e = 0; e < XP_MAXQ; ++e) { m1[e] = INFINITY; m2[e] = INFINITY; i1[e] = 0xFFFFFFFFu; }
+
+  const bool f32 = vi.dtype == DT_F32;                      // fp32 rows: asynchronous 16-byte copies; uchar-stored rows (integer-valued view of a
+  const int ntile = ((int)p.m_i + XP_ROWS - 1) / XP_ROWS;   // mixed pair): converted on a synchronous load
+  auto load_tile = [&](int t, int buf) {
+    float* tile = xp_tiles + buf * (XP_ROWS * XP_LD);
+    const uint32_t row0 = (uint32_t)t * XP_ROWS;
+    for (int k = tid; k < XP_ROWS * 32; k += XP_THREADS) {  // 64 rows x 32 chunks of 16 B, coalesced
+      const int rr = k >> 5, c4 = k & 31;
+      const bool valid = row0 + rr < p.m_i;
+      if (f32) {
+        cp_async16(&tile[rr * XP_LD + c4 * 4], reinterpret_cast<const float4*>(vi.raw) + (valid ? ((size_t)(row0 + rr) * 32 + c4) : 0), valid);
+      } else {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + rr < p.m_i) {
-          const size_t base = (size_t)(row0 + rr) * 128 + c4 * 4;
-          if (vi.dtype == DT_F32) v = __ldg(reinterpret_cast<const float4*>(vi.raw) + (base >> 2));
-          else v = make_float4(view_elem(vi, base), view_elem(vi, base + 1), view_elem(vi, base + 2), view_elem(vi, base + 3));
-        }
+        if (valid) { const size_t base = (size_t)(row0 + rr) * 128 + c4 * 4; v = make_float4(view_elem(vi, base), view_elem(vi, base + 1), view_elem(vi, base + 2), view_elem(vi, base + 3)); }
         *reinterpret_cast<float4*>(&tile[rr * XP_LD + c4 * 4]) = v;
       }
-      __syncthreads();
-      float s[XP_MAXQ];
-#pragma unroll
-      for (int e = 0; e < XP_MAXQ; ++e) s[e] = 0.f;
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float tv = tile[r * XP_LD + 4 * t + l];
-#pragma unroll
-        for (int e = 0; e < XP_MAXQ; ++e) { const float d = __fsub_rn(qr[e][t], tv); s[e] = __fadd_rn(s[e], __fmul_rn(d, d)); }   // an unused query slot holds zeros
-      }
-      const uint32_t row = row0 + r;
-#pragma unroll
-      for (int e = 0; e < XP_MAXQ; ++e) {
-        if (e < ne) {
-          const float s1 = __shfl_xor_sync(gmask, s[e], 1);
-          const float pr = (l & 1) ? __fadd_rn(s1, s[e]) : __fadd_rn(s[e], s1);          // s0+s1 on lanes 0,1 ; s2+s3 on lanes 2,3
-          const float s01 = __shfl_sync(gmask, pr, 0, 4);
-          const float s2 = __shfl_sync(gmask, s[e], 2, 4), s3 = __shfl_sync(gmask, s[e], 3, 4);
-          const float d = __fadd_rn(__fadd_rn(s01, s2), s3);
-          if (l == 0 && row < p.m_i) {
-            if (d < m1[e] || (d == m1[e] && row < i1[e])) { m2[e] = m1[e]; m1[e] = d; i1[e] = row; } else m2[e] = fminf(m2[e], d);
-          }
-        }
-      }
     }
-    // reduce the per-thread top-2 (held by the l == 0 threads) over the block
+    cp_async_commit();
+  };
+  load_tile(0, 0);
+  for (int t = 0; t < ntile; ++t) {
+    if (t + 1 < ntile) { load_tile(t + 1, (t + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();                                        // tile t is complete for every thread
+    const float* tile = xp_tiles + (t & 1) * (XP_ROWS * XP_LD);
+    float s[XP_MAXQ];
+#pragma unroll
+    for (int e = 0; e < XP_MAXQ; ++e) s[e] = 0.f;
+#pragma unroll
+    for (int tt = 0; tt < 32; ++tt) {
+      const float tv = tile[r * XP_LD + 4 * tt + l];
+#pragma unroll
+      for (int e = 0; e < XP_MAXQ; ++e) { const float d = __fsub_rn(qr[e][tt], tv); s[e] = __fadd_rn(s[e], __fmul_rn(d, d)); }   // an unused query slot holds zeros
+    }
+    const uint32_t row = (uint32_t)t * XP_ROWS + r;
 #pragma unroll
     for (int e = 0; e < XP_MAXQ; ++e) {
-      float a1 = m1[e], a2 = m2[e]; uint32_t ai = i1[e];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const float o1 = __shfl_xor_sync(0xffffffffu, a1, o), o2 = __shfl_xor_sync(0xffffffffu, a2, o);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, ai, o);
-        if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
+      const float s1 = __shfl_xor_sync(gmask, s[e], 1);
+      const float pr = (l & 1) ? __fadd_rn(s1, s[e]) : __fadd_rn(s[e], s1);          // s0+s1 on lanes 0,1 ; s2+s3 on lanes 2,3
+      const float s01 = __shfl_sync(gmask, pr, 0, 4);
+      const float s2 = __shfl_sync(gmask, s[e], 2, 4), s3 = __shfl_sync(gmask, s[e], 3, 4);
+      const float d = __fadd_rn(__fadd_rn(s01, s2), s3);
+      if (l == 0 && row < p.m_i) {
+        if (d < m1[e] || (d == m1[e] && row < i1[e])) { m2[e] = m1[e]; m1[e] = d; i1[e] = row; } else m2[e] = fminf(m2[e], d);
       }
-      if (lane == 0) { rm1[e][warp] = a1; rm2[e][warp] = a2; ri1[e][warp] = ai; }
     }
-    __syncthreads();
-    if (tid < ne) {
-      float a1 = rm1[tid][0], a2 = rm2[tid][0]; uint32_t ai = ri1[tid][0];
-      for (int w2 = 1; w2 < XP_THREADS / 32; ++w2) {
-        const float o1 = rm1[tid][w2], o2 = rm2[tid][w2]; const uint32_t oi = ri1[tid][w2];
-        if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
-      }
-      const uint4 ent = pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + tid];
-      if (a1 < __fmul_rn(ratio_sq, a2)) {                                // matching/filters.hpp:60
-        const int slot = ent.w ? (int)ent.z : atomicAdd(&cand_count[blockIdx.x], 1);
-        cands[p.cand_base + slot] = Cand{ent.y, ai, a1, a2};
-      }
+    __syncthreads();                                        // everyone is done with buffer t & 1 before tile t + 2 lands in it
+  }
+  // reduce the per-thread top-2 (held by the l == 0 threads) over the block
+#pragma unroll
+  for (int e = 0; e < XP_MAXQ; ++e) {
+    float a1 = m1[e], a2 = m2[e]; uint32_t ai = i1[e];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, a1, o), o2 = __shfl_xor_sync(0xffffffffu, a2, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, ai, o);
+      if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
+    }
+    if (lane == 0) { rm1[e][warp] = a1; rm2[e][warp] = a2; ri1[e][warp] = ai; }
+  }
+  __syncthreads();
+  if (tid < ne) {
+    float a1 = rm1[tid][0], a2 = rm2[tid][0]; uint32_t ai = ri1[tid][0];
+    for (int w2 = 1; w2 < XP_THREADS / 32; ++w2) {
+      const float o1 = rm1[tid][w2], o2 = rm2[tid][w2]; const uint32_t oi = ri1[tid][w2];
+      if (o1 < a1 || (o1 == a1 && oi < ai)) { a2 = fminf(a1, o2); a1 = o1; ai = oi; } else a2 = fminf(a2, o1);
+    }
+    const uint4 ent = pair_list[(size_t)blockIdx.x * FB_PER_PAIR + e0 + tid];
+    if (a1 < __fmul_rn(ratio_sq, a2)) {                                // matching/filters.hpp:60
+      const int slot = ent.w ? (int)ent.z : atomicAdd(&cand_count[blockIdx.x], 1);
+      cands[p.cand_base + slot] = Cand{ent.y, ai, a1, a2};
     }
   }
 }
