@@ -64,7 +64,7 @@ def test_round2_bench_lines():
         m = _line(name)
         assert m["n_gpus"] == n and m["scaling"] == "weak" and abs(m["config"]["pairs_per_gpu"] - 4950) < 60
         assert m["config"]["max_views_on_a_gpu"] <= {4: 0.76, 8: 0.51}[n] * bench_images(n) + 1
-        assert m["e2e"]["value"] > {4: 0.85, 8: 0.75}[n] * n * 0.93 * d["e2e"]["value"]          # measured with the build before the last kernel change
+        assert m["e2e"]["value"] > {4: 0.80, 8: 0.75}[n] * n * d["e2e"]["value"]          # the 4-GPU line predates the last kernel change (its own 1-GPU e2e was 73 k)
     c2 = _line("r02_bench_config2_8gpu.json"); c3 = _line("r02_bench_config3_4gpu.json")
     assert c2["n_gpus"] == 8 and c2["scaling"] == "strong" and "1000 synthetic images" in c2["config"]["workload"] and c2["config"]["max_views_on_a_gpu"] == 500
     assert c3["n_gpus"] == 4 and c3["scaling"] == "strong" and "500 synthetic images" in c3["config"]["workload"] and c3["roofline"]["bound"] == "hbm"
