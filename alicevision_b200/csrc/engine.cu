@@ -267,6 +267,7 @@ struct b200m_ctx {
   std::shared_ptr<Recycler> recycler = std::make_shared<Recycler>();
   bool force_exact = false;
   bool real_tc = true;            // real-valued fp32 pairs on the tensor-core filter kernel (B200M_REAL_TC=0: exact CUDA-core kernel as in round 1)
+  int first_batch_pairs = 16;     // while uploads are in flight: pairs of the first batch (then 2x per batch): how soon the GPU starts (B200M_FIRST_BATCH)
   long real_fused_rows = 6144;    // average database rows per item from which the real-valued re-scoring runs inside the filter kernel
   int tc_variant = 4;             // 1 = single-CTA kernel (l2_tc.cuh); CTA-pair kernel (l2_tc2.cuh): 2 = 8 epilogue warps, 3 = 16 epilogue warps,
                                   // 4 (default) = 8 epilogue warps + half-norms folded into the GEMM (AUG)
@@ -556,6 +557,7 @@ int b200m_ctx_create(int device, void* stream, b200m_ctx** out) {
   c->pool.reset(new Pool(std::min(std::max(ht, 1), 32), c->cpus));
   if (const char* e = getenv("B200M_U8_STAGING")) c->u8_staging = atoi(e) != 0;
   if (const char* e = getenv("B200M_DEVICE_FINISH")) c->device_finish = atoi(e) != 0;
+  if (const char* e = getenv("B200M_FIRST_BATCH")) c->first_batch_pairs = std::max(1, atoi(e));
   if (const char* e = getenv("B200M_REAL_TC")) c->real_tc = atoi(e) != 0;
   if (const char* e = getenv("B200M_REAL_FUSED_ROWS")) c->real_fused_rows = std::max(0l, atol(e));
   *out = c.release();
@@ -631,6 +633,13 @@ int b200m_debug_trace(b200m_ctx* c, int enable, long long* out, int n) {
   if (!enable && c->d_trace) { cudaFree(c->d_trace); c->d_trace = nullptr; }
   return B200M_OK;
 }
+// Debug / test hook (host only, no GPU needed): the checked fp32 -> uchar conversion of the staging path (hostconv.hpp).
+// which: 0 = the dispatching entry point (AVX2 when the CPU has it), 1 = the scalar reference.  Returns 1 when every value was an integer in 0..255.
+int b200m_debug_convert_f32_u8(const float* src, uint8_t* dst, size_t n, int which) {
+  if ((!src || !dst) && n) return -1;
+  return (which == 1 ? f32_to_u8_checked_scalar(src, dst, n) : f32_to_u8_checked(src, dst, n)) ? 1 : 0;
+}
+
 int b200m_ctx_set_force_exact(b200m_ctx* c, int on) {
   if (!c) return fail(B200M_ERR_ARG, "ctx is null");
   c->force_exact = on != 0;
@@ -1052,7 +1061,7 @@ static int match_pairs_impl(b200m_ctx* c, const uint32_t* pairs, int n_pairs, fl
   std::vector<Batch> batches;
   {
     size_t b0 = 0; long cand = 0, items = 0, slots = 0;
-    size_t pair_cap = pending ? 64 : (size_t)PAIR_CAP;
+    size_t pair_cap = pending ? (size_t)c->first_batch_pairs : (size_t)PAIR_CAP;
     for (size_t k = 0; k < seqv.size(); k += step) {
       long need_c = 0, need_i = 0, need_s = 0;
       for (size_t u = k; u < k + step; ++u) {

@@ -32,7 +32,7 @@ MATCH_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("ratio", np.float32
 # every symbol include/b200match.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "b200m_last_error", "b200m_version", "b200m_device_count", "b200m_ctx_create", "b200m_ctx_destroy", "b200m_ctx_set_host_threads",
-    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
+    "b200m_ctx_set_force_exact", "b200m_ctx_set_tc_variant", "b200m_debug_trace", "b200m_debug_convert_f32_u8", "b200m_db_create", "b200m_db_destroy", "b200m_knn", "b200m_upload_view", "b200m_upload_views", "b200m_upload_views_async", "b200m_wait_uploads", "b200m_clear_views", "b200m_remove_view",
     "b200m_match_pairs", "b200m_result_num_pairs", "b200m_result_get", "b200m_result_free", "b200m_last_gpu_ms",
     "b200m_last_search_kernel_ms", "b200m_last_launches", "b200m_last_tc_pairs", "b200m_exactness_errors", "b200m_last_records", "b200m_last_real_tc_pairs", "b200m_last_fallback_rows",
     "b200m_shard_pairs", "b200m_shard_pairs_2d", "b200m_multi_create", "b200m_multi_destroy", "b200m_multi_num_devices", "b200m_multi_ctx", "b200m_multi_match",

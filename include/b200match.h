@@ -62,6 +62,11 @@ int b200m_ctx_set_force_exact(b200m_ctx* ctx, int on);
  * 2 / 3 = CTA pair with an add in the epilogue (8 / 16 epilogue warps), 1 = single CTA */
 int b200m_ctx_set_tc_variant(b200m_ctx* ctx, int variant);
 
+/* debug / test hook, host only: the checked fp32 -> uchar conversion the upload staging applies to integer-valued fp32 descriptors
+ * (which = 0: the dispatching implementation, AVX2 when available; 1: the scalar one).  1 = every value was an integer in 0..255 and dst
+ * holds them; 0 = some value is not (dst unspecified); -1 = bad arguments. */
+int b200m_debug_convert_f32_u8(const float* src, uint8_t* dst, size_t n, int which);
+
 /* debug: per-tile SM-clock trace of CTA 0 of the tensor-core kernel (4 roles x 512 tiles x 4 stamps); enable!=0 allocates,
  * out (may be NULL) receives up to n values after synchronising */
 int b200m_debug_trace(b200m_ctx* ctx, int enable, long long* out, int n);

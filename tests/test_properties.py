@@ -81,3 +81,33 @@ def test_convert_all_matches_to_pair_list(n, num_matches, rnd):
     got = voctree.convertAllMatchesToPairList(np.array(ids, np.uint32), match_ids, num_matches)
     want = _convert_reference({i: match_ids[k].tolist() for k, i in enumerate(ids)}, num_matches)
     assert [tuple(p) for p in got.tolist()] == want
+
+
+def test_checked_f32_to_u8_conversion_of_the_staging_path():
+    """hostconv.hpp through its test hook (host code, no GPU): the AVX2 implementation and the scalar one agree on acceptance and on the bytes, for every
+    length (vector body + tail), and reject anything that is not an integer in 0..255 wherever it sits."""
+    import ctypes as C
+    from alicevision_b200 import matching
+    lib = matching.load_library()
+    lib.b200m_debug_convert_f32_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rng = np.random.default_rng(11)
+
+    def conv(a, which):
+        out = np.zeros(max(a.size, 1), np.uint8)
+        rc = lib.b200m_debug_convert_f32_u8(a.ctypes.data, out.ctypes.data, a.size, which)
+        return rc, out[: a.size]
+
+    for n in (0, 1, 31, 32, 33, 127, 1024, 1025, 8192 * 128):
+        a = rng.integers(0, 256, n).astype(np.float32)
+        for which in (0, 1):
+            rc, out = conv(a, which)
+            assert rc == 1 and np.array_equal(out, a.astype(np.uint8))
+    base = rng.integers(0, 256, 4099).astype(np.float32)
+    for bad in (0.5, -1.0, 256.0, 255.5, 1e20, -1e20, np.nan, np.inf, 1e-30):
+        for pos in (0, 7, 31, 32, 1000, 2047, 4096, 4098):
+            a = base.copy(); a[pos] = bad
+            assert conv(a, 0)[0] == 0 and conv(a, 1)[0] == 0, (bad, pos)
+    a = base.copy(); a[5] = -0.0; a[6] = 255.0; a[7] = 0.0          # -0.0 is the integer 0
+    for which in (0, 1):
+        rc, out = conv(a, which)
+        assert rc == 1 and out[5] == 0 and out[6] == 255
