@@ -153,6 +153,44 @@ score_postings_kernel(const unsigned long long* __restrict__ ukeys, const int* _
   }
 }
 
+// ---- K6b: "inversedWeightedCommonPoints" (VocabularyTree.cpp:192-247): score(a, b) = sum over the common words, in ASCENDING word id, of
+// (1.f / min(count_a, count_b)) * weight[word] - a float accumulation whose order matters, so every (a, b) is summed by ONE thread that merges the two
+// documents' sorted (word, count) lists exactly like the reference's std::map walk (division, multiplication and addition rounded separately).
+// Entries: the unique (document, word) pairs sorted by document then word; doc_start[d] .. doc_start[d + 1] is document d's list.
+__global__ void doc_keys_kernel(const unsigned long long* __restrict__ ukeys, int n, unsigned long long* __restrict__ dkeys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dkeys[i] = (ukeys[i] << 32) | (ukeys[i] >> 32);            // (word, doc) -> (doc, word)
+}
+__global__ void doc_starts_kernel(const unsigned long long* __restrict__ dkeys, int n, int n_docs, int* __restrict__ doc_start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int prev = i == 0 ? -1 : (int)(dkeys[i - 1] >> 32);
+  const int cur = i == n ? n_docs : (int)(dkeys[i] >> 32);
+  for (int d = prev + 1; d <= cur; ++d) doc_start[d] = i;                // documents without words get an empty range
+}
+__global__ void __launch_bounds__(128)
+weighted_pairs_kernel(const unsigned long long* __restrict__ dkeys, const int* __restrict__ dcounts, const int* __restrict__ doc_start,
+                      const float* __restrict__ weights, int n_docs, float* __restrict__ S) {
+  const int a = blockIdx.y;
+  const int b = a + blockIdx.x * blockDim.x + threadIdx.x;               // upper triangle incl. the diagonal
+  if (b >= n_docs) return;
+  int i = doc_start[a]; const int ie = doc_start[a + 1];
+  int j = doc_start[b]; const int je = doc_start[b + 1];
+  float score = 0.f;
+  while (i < ie && j < je) {
+    const unsigned wi = (unsigned)(dkeys[i] & 0xffffffffull), wj = (unsigned)(dkeys[j] & 0xffffffffull);
+    if (wj < wi) ++j;
+    else if (wi < wj) ++i;
+    else {
+      const int m = min(dcounts[i], dcounts[j]);
+      score = __fadd_rn(score, __fmul_rn(__fdiv_rn(1.f, (float)m), weights[wi]));
+      ++i; ++j;
+    }
+  }
+  S[(size_t)a * n_docs + b] = score;
+  S[(size_t)b * n_docs + a] = score;
+}
+
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -320,10 +358,11 @@ int b200v_db_query_all(b200v_db* db, size_t numImageQuery, const char* distanceM
                        size_t* n_keep_out) {
   if (!db || !distanceMethod) return set_error(B200M_ERR_ARG, "bad arguments");
   const std::string method(distanceMethod);
-  int mode;                                        // which integer statistic the GPU accumulates
+  int mode;                                        // which statistic the GPU accumulates: 0 / 1 integer counts over the inverted file, 2 the weighted float sum per document pair
   if (method == "strongCommonPoints") mode = 1;
   else if (method == "commonPoints" || method == "classic") mode = 0;
-  else if (method == "weightedStrongCommonPoints" || method == "inversedWeightedCommonPoints")
+  else if (method == "inversedWeightedCommonPoints") mode = 2;
+  else if (method == "weightedStrongCommonPoints")
     return set_error(B200M_ERR_UNSUPPORTED, "distance method " + method + " is not implemented (the reference's own loop for it reads past the end of the histograms, VocabularyTree.cpp:153-171)");
   else return set_error(B200M_ERR_ARG, "distance method " + method + " unknown!");     // std::invalid_argument in the reference (:251-253)
   const size_t n_docs = db->docs.size();
@@ -345,6 +384,8 @@ int b200v_db_query_all(b200v_db* db, size_t numImageQuery, const char* distanceM
   }
   db->last_scores.assign(n_docs * n_docs, 0);
   db->last_n = (int64_t)n_docs;
+  std::vector<float> wscores;                      // mode 2: the weighted scores (the integer matrix stays zero)
+  if (mode == 2) wscores.assign(n_docs * n_docs, 0.f);
   if (total > 0) {
     if (total > 0x7fffffffull) return set_error(B200M_ERR_UNSUPPORTED, "more than 2^31 features in the database");
     const int n = (int)total;
@@ -380,11 +421,32 @@ int b200v_db_query_all(b200v_db* db, size_t numImageQuery, const char* distanceM
     VCK(cudaMemcpyAsync(&nw, d_nw.p, 4, cudaMemcpyDeviceToHost, st));
     VCK(cudaStreamSynchronize(st));
     VCK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_len.as<int>(), d_start.as<int>(), nw, st));
+    if (mode == 2) {
+      // per-document sorted (word, count) lists: re-key the unique pairs by (document, word), sort them with their counts
+      DevBuf d_dk, d_dk2, d_dc2, d_ds, d_wt, d_tmp2;
+      if ((rc = d_dk.alloc((size_t)nu * 8)) || (rc = d_dk2.alloc((size_t)nu * 8)) || (rc = d_dc2.alloc((size_t)nu * 4)) || (rc = d_ds.alloc((n_docs + 2) * 4)) ||
+          (rc = d_wt.alloc(db->word_weights.size() * 4)))
+        return rc;
+      VCK(cudaMemcpyAsync(d_wt.p, db->word_weights.data(), db->word_weights.size() * 4, cudaMemcpyHostToDevice, st));
+      doc_keys_kernel<<<(nu + 255) / 256, 256, 0, st>>>(d_ukeys.as<unsigned long long>(), nu, d_dk.as<unsigned long long>());
+      size_t tb3 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb3, d_dk.as<unsigned long long>(), d_dk2.as<unsigned long long>(), d_cnt.as<int>(), d_dc2.as<int>(), nu, 0, 64, st);
+      if ((rc = d_tmp2.alloc(tb3))) return rc;
+      VCK(cub::DeviceRadixSort::SortPairs(d_tmp2.p, tb3, d_dk.as<unsigned long long>(), d_dk2.as<unsigned long long>(), d_cnt.as<int>(), d_dc2.as<int>(), nu, 0, 64, st));
+      doc_starts_kernel<<<(nu + 1 + 255) / 256, 256, 0, st>>>(d_dk2.as<unsigned long long>(), nu, (int)n_docs, d_ds.as<int>());
+      weighted_pairs_kernel<<<dim3((unsigned)((n_docs + 127) / 128), (unsigned)n_docs), 128, 0, st>>>(d_dk2.as<unsigned long long>(), d_dc2.as<int>(), d_ds.as<int>(), d_wt.as<float>(),
+                                                                                                  (int)n_docs, reinterpret_cast<float*>(d_S.p));
+      VCK(cudaGetLastError());
+      VCK(cudaEventRecord(db->e1, st));
+      VCK(cudaMemcpyAsync(wscores.data(), d_S.p, n_docs * n_docs * 4, cudaMemcpyDeviceToHost, st));
+      VCK(cudaStreamSynchronize(st));
+    } else {
     score_postings_kernel<<<(int)(((size_t)nw * 32 + 255) / 256), 256, 0, st>>>(d_ukeys.as<unsigned long long>(), d_cnt.as<int>(), d_start.as<int>(), d_len.as<int>(), nw, mode, (int)n_docs, d_S.as<int>());
     VCK(cudaGetLastError());
     VCK(cudaEventRecord(db->e1, st));
     VCK(cudaMemcpyAsync(db->last_scores.data(), d_S.p, n_docs * n_docs * 4, cudaMemcpyDeviceToHost, st));
     VCK(cudaStreamSynchronize(st));
+    }
     float ms = 0.f;
     VCK(cudaEventElapsedTime(&ms, db->e0, db->e1));
     db->last_gpu_ms = ms;
@@ -397,7 +459,8 @@ int b200v_db_query_all(b200v_db* db, size_t numImageQuery, const char* distanceM
     const int32_t* row = db->last_scores.data() + q * n_docs;
     for (size_t d = 0; d < n_docs; ++d) {
       float dist;
-      if (method == "classic") dist = (float)(nfeat[q] + nfeat[d] - 2 * (int64_t)row[d]);     // sum |c1 - c2| = n1 + n2 - 2 sum min(c1, c2); integers < 2^24
+      if (mode == 2) dist = -wscores[q * n_docs + d];                                           // distance = -score, VocabularyTree.cpp:246
+      else if (method == "classic") dist = (float)(nfeat[q] + nfeat[d] - 2 * (int64_t)row[d]);     // sum |c1 - c2| = n1 + n2 - 2 sum min(c1, c2); integers < 2^24
       else dist = -(float)row[d];
       m[d] = DocMatch{ids[d], dist};
     }

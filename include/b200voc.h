@@ -5,7 +5,7 @@
  *
  *   voctree/VocabularyTree.hpp:169-196    VocabularyTree::quantize   (tree descent, L2 in double, first minimum wins)
  *   voctree/VocabularyTree.hpp:74-81      computeSparseHistogram
- *   voctree/VocabularyTree.cpp:22-258     sparseDistance  ("classic", "commonPoints", "strongCommonPoints")
+ *   voctree/VocabularyTree.cpp:22-258     sparseDistance  ("classic", "commonPoints", "strongCommonPoints", "inversedWeightedCommonPoints")
  *   voctree/Database.cpp:44-137,145-157   Database::insert / find / computeTfIdfWeights
  *   voctree/databaseIO.tcc:23-49          populateDatabase
  *   imageMatching/ImageMatching.cpp:107-143,191-238   convertAllMatchesToPairList / generateFromVoctree (mode a/a)
@@ -64,7 +64,8 @@ int b200v_db_compute_tfidf(b200v_db* db, float default_weight, float* weights);
  * numImageQuery == 0 means "all" (ImageMatching.cpp:198-201).  Outputs are row-major n_docs x n_keep with
  * n_keep = min(numImageQuery, n_docs): query_ids (ascending doc ids, the std::map walk), match ids and scores in ranked
  * order (score = sparseDistance: smaller is better, negative for the *CommonPoints methods).
- * distanceMethod: "classic", "commonPoints" or "strongCommonPoints" (the reference's default). */
+ * distanceMethod: "classic", "commonPoints", "strongCommonPoints" (the reference's default) or "inversedWeightedCommonPoints" (float sum in ascending word
+ * order per document pair, one thread per pair; "weightedStrongCommonPoints" is undefined behaviour in the reference, VocabularyTree.cpp:153-171, and is refused). */
 int b200v_db_query_all(b200v_db* db, size_t numImageQuery, const char* distanceMethod, uint32_t* query_ids, uint32_t* match_ids, float* scores,
                        size_t* n_keep);
 /* the raw all-against-all integer score matrix of the last b200v_db_query_all (n_docs x n_docs, row = query): for tests / reuse */

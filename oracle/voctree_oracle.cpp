@@ -61,8 +61,8 @@ struct Tree {
     return index - (int32_t)word_start;
   }
 };
-// voctree/VocabularyTree.cpp:22-258, the three methods whose loops are well defined
-float sparseDistance(const SparseHistogram& v1, const SparseHistogram& v2, const std::string& distanceMethod) {
+// voctree/VocabularyTree.cpp:22-258, the four methods whose loops are well defined ("weightedStrongCommonPoints" dereferences end iterators, :153-171)
+float sparseDistance(const SparseHistogram& v1, const SparseHistogram& v2, const std::string& distanceMethod, const std::vector<float>& word_weights) {
   float distance = 0.f; const float epsilon = 0.001f;
   auto i1 = v1.cbegin(), i1e = v1.cend(); auto i2 = v2.cbegin(), i2e = v2.cend();
   if (distanceMethod == "classic") {
@@ -88,6 +88,16 @@ float sparseDistance(const SparseHistogram& v1, const SparseHistogram& v2, const
       else if (i1->first < i2->first) ++i1;
       else { if ((std::fabs(i1->second.size() - 1.f) < epsilon) && (std::fabs(i2->second.size() - 1.f) < epsilon)) score += 1; ++i1; ++i2; }
     }
+    distance = -score;
+  } else if (distanceMethod == "inversedWeightedCommonPoints") {                                   // :192-247
+    float score = 0.f;
+    std::map<int, int> counter;
+    while (i1 != i1e && i2 != i2e) {
+      if (i2->first < i1->first) ++i2;
+      else if (i1->first < i2->first) ++i1;
+      else { counter[i1->first] += std::min(i1->second.size(), i2->second.size()); ++i1; ++i2; }
+    }
+    for (const auto elem : counter) score += (1.f / elem.second) * word_weights[elem.first];    // ascending word id, float accumulation
     distance = -score;
   } else {
     return std::numeric_limits<float>::quiet_NaN();
@@ -121,7 +131,7 @@ struct Database {                                                  // voctree/Da
 #ifdef VOC_USE_REFERENCE
       const float distance = voctree::sparseDistance(query, document.second, method, word_weights);
 #else
-      const float distance = sparseDistance(query, document.second, method);
+      const float distance = sparseDistance(query, document.second, method, word_weights);
 #endif
       matches.push_back(DocMatch{document.first, distance});
     }

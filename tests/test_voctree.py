@@ -34,7 +34,7 @@ def tree(seed=4, invalid_tail=1):
 
 
 @pytest.mark.skipif(len(kinds()) < 2, reason="needs both the compiled reference and the port")
-@pytest.mark.parametrize("method", ["strongCommonPoints", "commonPoints", "classic"])
+@pytest.mark.parametrize("method", ["strongCommonPoints", "commonPoints", "classic", "inversedWeightedCommonPoints"])
 def test_port_equals_reference(method, tmp_path):
     R, P = oracle.VoctreeOracle("ref"), oracle.VoctreeOracle("port")
     c, v = tree()
@@ -119,7 +119,7 @@ def test_gpu_quantize_equals_oracle(invalid_tail):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", ["strongCommonPoints", "commonPoints", "classic"])
+@pytest.mark.parametrize("method", ["strongCommonPoints", "commonPoints", "classic", "inversedWeightedCommonPoints"])
 def test_gpu_image_matching_equals_oracle(method):
     from alicevision_b200 import voctree
     O = oracle.VoctreeOracle(kinds()[0])
@@ -140,6 +140,7 @@ def test_gpu_image_matching_equals_oracle(method):
     assert np.array_equal(got_pairs, O.image_matching(K, L, c, v, d, 0, 4, method)[4])
     S = db.last_scores()
     assert S.shape == (len(d), len(d)) and np.array_equal(S, S.T) and db.last_gpu_ms() > 0
+    assert (S.any() != (method == "inversedWeightedCommonPoints"))       # the integer statistic exists for the three counting methods only
     with pytest.raises(Exception):
         db.find_all(0, "weightedStrongCommonPoints")
     with pytest.raises(Exception):
