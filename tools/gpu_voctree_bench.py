@@ -27,9 +27,14 @@ q, ids, sc = db.find_all(a.neighbours)
 t3 = time.perf_counter()
 pairs = voctree.convertAllMatchesToPairList(q, ids, a.neighbours)
 t4 = time.perf_counter()
+tw0 = time.perf_counter()
+qw, idsw, scw = db.find_all(a.neighbours, "inversedWeightedCommonPoints")
+tw1 = time.perf_counter()
+weighted = {"query_all_ms": 1e3 * (tw1 - tw0), "scoring_kernels_ms": db.last_gpu_ms()}
 out = {"images": a.images, "features": a.features, "tree": f"K={a.k} L={a.levels} ({a.k ** a.levels} words)", "pairs": int(len(pairs)),
        "gpu": {"populate_ms": 1e3 * (t1 - t0), "tfidf_ms": 1e3 * (t2 - t1), "query_all_ms": 1e3 * (t3 - t2), "scoring_kernels_ms": db.last_gpu_ms(),
-               "pair_list_ms": 1e3 * (t4 - t3), "total_ms": 1e3 * (t4 - t0), "images_per_s": a.images / (t4 - t0)}}
+               "pair_list_ms": 1e3 * (t4 - t3), "total_ms": 1e3 * (t4 - t0), "images_per_s": a.images / (t4 - t0)},
+       "gpu_inversedWeightedCommonPoints": weighted}
 if a.no_cpu:
     print(json.dumps(out)); sys.exit(0)
 # CPU oracle (compiled reference when present) on a bounded sample, extrapolated
